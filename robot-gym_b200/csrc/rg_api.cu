@@ -1,0 +1,276 @@
+// C-ABI entry points (include/rg_cuda.h): argument validation, one-time table setup, launches.
+#include "rg_common.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+std::mutex g_ws_mutex;
+std::unordered_map<const void*, int> g_ws_horizon;   // prepared MPC workspaces -> horizon
+}  // namespace
+
+int rg_mpc_workspace_horizon(const void* workspace, int* horizon) {
+  {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    auto it = g_ws_horizon.find(workspace);
+    if (it != g_ws_horizon.end()) { *horizon = it->second; return RG_OK; }
+  }
+  // not prepared through this process' rg_mpc_setup (e.g. a copied workspace): read the header
+  RgMpcDev hdr;
+  int rc = rg_check_cuda(cudaMemcpy(&hdr, workspace, offsetof(RgMpcDev, inv_mass), cudaMemcpyDeviceToHost),
+                         "MPC workspace header read");
+  if (rc != RG_OK) return rc;
+  if (hdr.magic != RG_WS_MAGIC_MPC) { rg_set_error("workspace was not prepared by rg_mpc_setup"); return RG_ERR_WORKSPACE; }
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  g_ws_horizon[workspace] = hdr.horizon;
+  *horizon = hdr.horizon;
+  return RG_OK;
+}
+
+void rg_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int rg_check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return RG_OK;
+  rg_set_error("%s: %s", what, cudaGetErrorString(e));
+  return RG_ERR_CUDA;
+}
+
+void rg_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+extern "C" uint64_t rg_launch_count(void) { return g_launches.load(); }
+extern "C" const char* rg_last_error(void) { return g_err; }
+extern "C" const char* rg_version(void) { return "rg_cuda 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------------
+// Host-side horizon tables: generalised symmetric eigenproblem c2 U = c1 U diag(gamma), U^T c1 U = I
+// via Cholesky of c1 + cyclic Jacobi on the reduced matrix (h <= 20, done once per setup).
+namespace {
+
+void horizon_tables(int h, std::vector<double>& c1, std::vector<double>& c2) {
+  c1.assign(h * h, 0.0);
+  c2.assign(h * h, 0.0);
+  for (int j = 0; j < h; ++j)
+    for (int k = 0; k < h; ++k) {
+      const int m = j > k ? j : k;
+      c1[j * h + k] = h - m;
+      double s = 0.0;
+      for (int i = m + 1; i <= h; ++i) s += (i - j - 0.5) * (i - k - 0.5);
+      c2[j * h + k] = s;
+    }
+}
+
+bool generalized_eigen(int h, const std::vector<double>& c1, const std::vector<double>& c2,
+                       double* u_out /* [j][t] row-major h*h */, double* gamma_out) {
+  // c1 = L L^T
+  std::vector<double> l(h * h, 0.0);
+  for (int i = 0; i < h; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double v = c1[i * h + j];
+      for (int k = 0; k < j; ++k) v -= l[i * h + k] * l[j * h + k];
+      if (i == j) {
+        if (!(v > 0.0)) return false;
+        l[i * h + i] = sqrt(v);
+      } else {
+        l[i * h + j] = v / l[j * h + j];
+      }
+    }
+  // S = L^-1 c2 L^-T
+  std::vector<double> tmp(h * h), s(h * h);
+  for (int c = 0; c < h; ++c)          // solve L X = c2 (column by column)
+    for (int i = 0; i < h; ++i) {
+      double v = c2[i * h + c];
+      for (int k = 0; k < i; ++k) v -= l[i * h + k] * tmp[k * h + c];
+      tmp[i * h + c] = v / l[i * h + i];
+    }
+  for (int r = 0; r < h; ++r)          // solve S L^T = X  <=>  L S^T = X^T
+    for (int i = 0; i < h; ++i) {
+      double v = tmp[r * h + i];
+      for (int k = 0; k < i; ++k) v -= l[i * h + k] * s[r * h + k];
+      s[r * h + i] = v / l[i * h + i];
+    }
+  for (int i = 0; i < h; ++i)
+    for (int j = 0; j < i; ++j) { const double m = 0.5 * (s[i * h + j] + s[j * h + i]); s[i * h + j] = s[j * h + i] = m; }
+  // cyclic Jacobi: S = Q diag(gamma) Q^T
+  std::vector<double> qm(h * h, 0.0);
+  for (int i = 0; i < h; ++i) qm[i * h + i] = 1.0;
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < h; ++i)
+      for (int j = 0; j < h; ++j) (i == j ? diag : off) += s[i * h + j] * s[i * h + j];
+    if (off <= 1e-30 * diag) break;
+    for (int p = 0; p < h - 1; ++p)
+      for (int q = p + 1; q < h; ++q) {
+        const double apq = s[p * h + q];
+        if (fabs(apq) < 1e-300) continue;
+        const double theta = (s[q * h + q] - s[p * h + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < h; ++k) {
+          const double skp = s[k * h + p], skq = s[k * h + q];
+          s[k * h + p] = c * skp - sn * skq;
+          s[k * h + q] = sn * skp + c * skq;
+        }
+        for (int k = 0; k < h; ++k) {
+          const double spk = s[p * h + k], sqk = s[q * h + k];
+          s[p * h + k] = c * spk - sn * sqk;
+          s[q * h + k] = sn * spk + c * sqk;
+        }
+        for (int k = 0; k < h; ++k) {
+          const double qkp = qm[k * h + p], qkq = qm[k * h + q];
+          qm[k * h + p] = c * qkp - sn * qkq;
+          qm[k * h + q] = sn * qkp + c * qkq;
+        }
+      }
+  }
+  // U = L^-T Q
+  for (int t = 0; t < h; ++t) {
+    gamma_out[t] = s[t * h + t];
+    for (int i = h - 1; i >= 0; --i) {
+      double v = qm[i * h + t];
+      for (int k = i + 1; k < h; ++k) v -= l[k * h + i] * u_out[k * h + t];
+      u_out[i * h + t] = v / l[i * h + i];
+    }
+  }
+  return true;
+}
+
+bool inv3(const double* m, double* o) {
+  const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+  const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+  if (fabs(det) < 1e-300) return false;
+  const double id = 1.0 / det;
+  o[0] = c00 * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+  o[3] = c01 * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  o[6] = c02 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+  return true;
+}
+
+}  // namespace
+
+extern "C" int rg_mpc_default_params(rg_mpc_params* p, double mass, const double* inertia9,
+                                     double desired_body_height, int horizon) {
+  if (!p || !inertia9) { rg_set_error("rg_mpc_default_params: NULL argument"); return RG_ERR_BAD_ARG; }
+  memset(p, 0, sizeof(*p));
+  p->mass = mass;
+  memcpy(p->inertia, inertia9, 9 * sizeof(double));
+  p->num_legs = 4;
+  p->horizon = horizon;
+  p->dt = 0.025;
+  const double w[13] = {5, 5, 0.2, 0, 0, 10, 0.5, 0.5, 0.2, 0.2, 0.2, 0.1, 0};
+  memcpy(p->weights, w, sizeof(w));
+  p->alpha = 1e-5;
+  for (int i = 0; i < 4; ++i) p->friction_coeffs[i] = 0.45;
+  p->gravity = 9.8;
+  p->fz_max = mass * 9.8 * 10.0;
+  p->fz_min = mass * 9.8 * 0.1;
+  p->desired_body_height = desired_body_height;
+  p->ipm_tol = 1e-6;
+  p->max_ipm_iters = 30;
+  p->max_polish_rounds = 3;
+  return RG_OK;
+}
+
+extern "C" int rg_workspace_bytes(int n_env, int horizon, int num_legs, size_t* bytes) {
+  if (!bytes || n_env < 0) { rg_set_error("rg_workspace_bytes: bad argument"); return RG_ERR_BAD_ARG; }
+  if (num_legs != 4) { rg_set_error("num_legs=%d unsupported (4 only)", num_legs); return RG_ERR_UNSUPPORTED; }
+  if (horizon != 5 && horizon != 10 && horizon != 20) {
+    rg_set_error("unsupported horizon %d (kernels are built for 5, 10, 20)", horizon);
+    return RG_ERR_UNSUPPORTED;
+  }
+  *bytes = (sizeof(RgMpcDev) + 255) & ~size_t(255);
+  return RG_OK;
+}
+
+extern "C" int rg_mpc_setup(const rg_mpc_params* p, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!p || !workspace) { rg_set_error("rg_mpc_setup: NULL argument"); return RG_ERR_BAD_ARG; }
+  size_t need = 0;
+  int rc = rg_workspace_bytes(0, p->horizon, p->num_legs, &need);
+  if (rc != RG_OK) return rc;
+  if (workspace_bytes < need) { rg_set_error("workspace too small: %zu < %zu", workspace_bytes, need); return RG_ERR_WORKSPACE; }
+  if (!(p->mass > 0) || !(p->dt > 0) || !(p->alpha > 0) || !(p->fz_max > p->fz_min) || !(p->fz_min >= 0)) {
+    rg_set_error("rg_mpc_setup: need mass>0, dt>0, alpha>0, 0<=fz_min<fz_max");
+    return RG_ERR_BAD_ARG;
+  }
+  for (int i = 0; i < 4; ++i)
+    if (!(p->friction_coeffs[i] > 0)) { rg_set_error("friction coefficient %d must be > 0", i); return RG_ERR_BAD_ARG; }
+  for (int i = 0; i < 13; ++i)
+    if (!(p->weights[i] >= 0)) { rg_set_error("weight %d must be >= 0", i); return RG_ERR_BAD_ARG; }
+  // K = c1 (x) K1 + c2 (x) K2 must be positive definite: every acceleration channel needs a
+  // velocity weight or (for the angular channels: all three) a position weight.
+  const bool ang_pos = p->weights[0] > 0 && p->weights[1] > 0 && p->weights[2] > 0;
+  for (int c = 0; c < 3; ++c) {
+    if (!(p->weights[6 + c] > 0) && !ang_pos) {
+      rg_set_error("weights leave angular channel %d unpenalised (need w[%d]>0 or w[0..2]>0)", c, 6 + c);
+      return RG_ERR_SINGULAR;
+    }
+    if (!(p->weights[9 + c] > 0) && !(p->weights[3 + c] > 0)) {
+      rg_set_error("weights leave linear channel %d unpenalised (need w[%d]>0 or w[%d]>0)", c, 9 + c, 3 + c);
+      return RG_ERR_SINGULAR;
+    }
+  }
+  RgMpcDev h;
+  memset(&h, 0, sizeof(h));
+  h.magic = RG_WS_MAGIC_MPC;
+  h.horizon = p->horizon;
+  h.max_ipm_iters = p->max_ipm_iters > 0 ? p->max_ipm_iters : 30;
+  h.max_polish_rounds = p->max_polish_rounds;
+  h.inv_mass = 1.0 / p->mass;
+  if (!inv3(p->inertia, h.inv_inertia)) { rg_set_error("inertia matrix is singular"); return RG_ERR_SINGULAR; }
+  h.dt = p->dt;
+  for (int i = 0; i < 6; ++i) { h.w_rho[i] = p->weights[i]; h.w_nu[i] = p->weights[6 + i]; }
+  h.alpha = p->alpha;
+  for (int i = 0; i < 4; ++i) h.mu[i] = p->friction_coeffs[i];
+  h.gravity = p->gravity;
+  h.fz_max = p->fz_max;
+  h.fz_min = p->fz_min;
+  h.height = p->desired_body_height;
+  h.ipm_tol = p->ipm_tol > 0 ? p->ipm_tol : 1e-6;
+  std::vector<double> c1, c2;
+  horizon_tables(p->horizon, c1, c2);
+  if (!generalized_eigen(p->horizon, c1, c2, h.eig_u, h.eig_gamma)) {
+    rg_set_error("horizon table factorisation failed");
+    return RG_ERR_SINGULAR;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = rg_check_cuda(cudaMemcpyAsync(workspace, &h, sizeof(h), cudaMemcpyHostToDevice, st), "rg_mpc_setup upload");
+  if (rc != RG_OK) return rc;
+  rc = rg_check_cuda(cudaStreamSynchronize(st), "rg_mpc_setup sync");
+  if (rc != RG_OK) return rc;
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  g_ws_horizon[workspace] = p->horizon;
+  return RG_OK;
+}
+
+extern "C" int rg_mpc_build_solve(const void* workspace, int n_env, const float* com_velocity_body,
+                                  const float* base_rpy, const float* base_rpy_rate,
+                                  const uint8_t* foot_contact_state, const float* foot_positions_base,
+                                  const float* command, const float* com_height, float* contact_forces,
+                                  float* horizon_forces, int32_t* solve_info, void* stream) {
+  if (!workspace || !com_velocity_body || !base_rpy || !base_rpy_rate || !foot_contact_state ||
+      !foot_positions_base || !command || !contact_forces) {
+    rg_set_error("rg_mpc_build_solve: NULL argument");
+    return RG_ERR_BAD_ARG;
+  }
+  if (n_env < 0) { rg_set_error("rg_mpc_build_solve: n_env < 0"); return RG_ERR_BAD_ARG; }
+  if (n_env == 0) return RG_OK;
+  int horizon = 0;
+  int rc = rg_mpc_workspace_horizon(workspace, &horizon);
+  if (rc != RG_OK) return rc;
+  return rg_launch_mpc((const RgMpcDev*)workspace, horizon, n_env, com_velocity_body, base_rpy, base_rpy_rate,
+                       foot_contact_state, foot_positions_base, command, com_height, 0, contact_forces, horizon_forces,
+                       solve_info, (cudaStream_t)stream);
+}

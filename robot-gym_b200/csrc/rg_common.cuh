@@ -1,0 +1,82 @@
+// Shared device/host definitions for the batched locomotion-controller kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "rg_cuda.h"
+
+#define RG_WS_MAGIC_MPC 0x52474d50u   // "RGMP"
+#define RG_WS_MAGIC_ROBOT 0x5247524fu // "RGRO"
+
+// Device image of rg_mpc_params + the horizon tables, as laid out in the MPC workspace.
+struct RgMpcDev {
+  uint32_t magic;
+  int32_t horizon;
+  int32_t max_ipm_iters;
+  int32_t max_polish_rounds;
+  double inv_mass;
+  double inv_inertia[9];   // body frame
+  double dt;
+  double w_rho[6];         // weights of (roll,pitch,yaw,x,y,z)
+  double w_nu[6];          // weights of (wx,wy,wz,vx,vy,vz)
+  double alpha;
+  double mu[4];
+  double gravity;
+  double fz_max, fz_min;
+  double height;
+  double ipm_tol;
+  // Generalised eigen-decomposition of the horizon coupling tables:
+  //   c1(j,k) = h - max(j,k), c2(j,k) = sum_{i>max(j,k)}^{h} (i-j-1/2)(i-k-1/2)
+  //   U^T c1 U = I,  U^T c2 U = diag(gamma);  eig_u is row-major [j][t].
+  double eig_u[RG_MAX_HORIZON * RG_MAX_HORIZON];
+  double eig_gamma[RG_MAX_HORIZON];
+};
+
+// Device image of rg_robot_params with the IK constants derived on the host.
+struct RgLegDev {
+  double p[3][3];
+  double r[3][9];
+  double axis[3][3];
+  double toe[3];
+  // closed-form IK constants (hip-joint frame), see rg_kinematics.cuh
+  double e0[3], e1[3], e2[3];   // orthonormal basis in the hip-link frame: e0 = hip axis, e1 = upper axis
+  double t1e0, t1e2, dconst;    // upper-joint offset along e0/e2 and the constant lateral offset D along e1
+  double l1, l2, phi2, psi;     // planar two-link lengths, phase of link 2, phase of the plane basis
+  double s2;                    // +1/-1: lower axis parallel/antiparallel to the upper axis
+  double sign_hip, sign_knee;
+};
+
+struct RgRobotDev {
+  uint32_t magic;
+  int32_t velocity_window;
+  RgLegDev legs[RG_NUM_LEGS];
+  double hip_positions[RG_NUM_LEGS][3];
+  double motor_offset[RG_NUM_MOTORS];
+  double motor_direction[RG_NUM_MOTORS];
+  double motor_kp[RG_NUM_MOTORS];
+  double motor_kd[RG_NUM_MOTORS];
+  double stance_duration[RG_NUM_LEGS];
+  double duty_factor[RG_NUM_LEGS];
+  double initial_leg_phase[RG_NUM_LEGS];
+  int32_t initial_leg_state[RG_NUM_LEGS];
+  int32_t next_leg_state[RG_NUM_LEGS];
+  double initial_state_ratio[RG_NUM_LEGS];
+  double contact_detection_phase_threshold;
+  double desired_height;
+  double foot_clearance;
+  double swing_kp[3];
+  double swing_max_clearance;
+};
+
+// host-side error plumbing (rg_api.cu)
+void rg_set_error(const char* fmt, ...);
+int rg_check_cuda(cudaError_t e, const char* what);
+void rg_count_launch();
+
+// launchers implemented in the .cu files
+struct rg_controller_state;
+int rg_launch_mpc(const RgMpcDev* ws, int horizon, int n_env, const float* com_vel, const float* rpy,
+                  const float* rpy_rate, const uint8_t* contacts, const float* feet, const float* command,
+                  const float* com_height, int zero_yaw, float* forces, float* horizon_forces, int32_t* info,
+                  cudaStream_t stream);
+// horizon stored in a prepared MPC workspace (host-side registry, falls back to a header read)
+int rg_mpc_workspace_horizon(const void* workspace, int* horizon);

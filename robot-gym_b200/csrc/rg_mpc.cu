@@ -1,0 +1,983 @@
+// Convex-MPC stance QP: one CTA per env, float64, everything on chip (sm_100a).
+//
+// Replaces mpc_osqp.ConvexMpc::ComputeContactForces of motion_imitation==0.0.5 (third-party;
+// call site robot_gym/controllers/mpc/mpc_controller.py:47-56,105).  The reference builds a
+// dense 13h x 3kh condensed system with a Pade matrix exponential and hands it to OSQP
+// (ADMM to 1e-3 + polish).  This kernel reaches the same unique optimum differently:
+//
+//  * [[A,B],[0,0]] is nilpotent of index 3, so the discretisation is exact in closed form and
+//    the state deviation depends on the forces only through the 6-dim acceleration
+//    a_t = B_nu u_t.  The condensed Hessian is  P = 2 alpha I + W^T K W  with
+//    W = I_h (x) B_nu (6h x 12h) and K = c1 (x) K1 + c2 (x) K2 (6h x 6h, Kronecker in time).
+//  * Newton systems (P + G^T D G) dx = r are solved through the Woodbury identity with the
+//    block-diagonal 3x3 part E = 2 alpha I + G^T D G:  only a 6h x 6h SPD matrix
+//    Psi = K^-1 + W E^-1 W^T is factorised (60 x 60 at h = 10 instead of 120 x 120).
+//  * K^-1 comes from a host-precomputed generalised eigen-decomposition of (c2, c1).
+//  * Mehrotra predictor-corrector interior point from a strictly feasible start to a loose
+//    tolerance, then an exact null-space active-set polish (the analogue of OSQP's polish),
+//    verified against primal feasibility and multiplier signs.
+//
+// Thread roles inside a CTA (NT = 32 * ceil(6h / 32) threads):
+//   "block" threads  tid < 4h : own one (time step, leg) force triple with its 10 slacks and
+//                               multipliers in registers; 4 adjacent lanes = the 4 legs of a step,
+//                               so per-step sums over legs are two __shfl_xor rounds.
+//   "row"   threads  tid < 6h : own one row of Psi during the Cholesky factorisation.
+//   warp 0                    : runs the two triangular sweeps with __shfl broadcasts.
+#include "rg_common.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+template <int H>
+struct Cfg {
+  static constexpr int N6 = 6 * H;
+  static constexpr int NB = 4 * H;
+  static constexpr int NT = ((N6 + 31) / 32) * 32;
+  static constexpr int NW = NT / 32;
+  static constexpr int NPSI = N6 * (N6 + 1) / 2;
+  static constexpr int NA = 3 * H;
+  static constexpr int NKA = NA * (NA + 1) / 2;
+  static constexpr int NKL = H * (H + 1) / 2;
+  static constexpr int RPL = (N6 + 31) / 32;   // Psi rows per lane in the triangular sweeps
+};
+
+template <int H>
+struct Smem {
+  double psi[Cfg<H>::NPSI];        // packed lower triangle, row-major
+  double kinv_ang[Cfg<H>::NKA];    // K^-1 angular block, packed, index a = 3 j + c
+  double kinv_lin[3][Cfg<H>::NKL]; // K^-1 linear channels, packed
+  double c2tab[H * H];
+  double gt[H * 6];                // g~ : gradient in acceleration space
+  double avec[H * 6];              // W u, right-hand sides and Woodbury solutions
+  double kvec[H * 6];              // K (W u)
+  double rdiag[Cfg<H>::N6];
+  double bang[4][9];               // A_leg = I_world^-1 [r_leg]x
+  double k2ang[9];
+  double k1[6];
+  double k2lin[3];
+  double qinv[H][9];               // (K1 + gamma_t K2)^-1 : 6 packed angular + 3 linear
+  double red[3][8];
+  int flag;
+};
+
+__device__ __forceinline__ int tri(int i, int k) { return i * (i + 1) / 2 + k; }
+
+__device__ __forceinline__ double c1f(int h, int j, int k) { return (double)(h - (j > k ? j : k)); }
+
+__device__ __forceinline__ double c2f(int h, int j, int k) {
+  // sum_{i=m+1}^{h} (i - j - 1/2)(i - k - 1/2)
+  const int m = j > k ? j : k;
+  const double a = j + 0.5, b = k + 0.5;
+  const double cnt = h - m;
+  const double s1 = 0.5 * ((double)h * (h + 1) - (double)m * (m + 1));
+  const double s2 = ((double)h * (h + 1) * (2 * h + 1) - (double)m * (m + 1) * (2 * m + 1)) / 6.0;
+  return s2 - (a + b) * s1 + a * b * cnt;
+}
+
+// ---- block-wide reductions (all threads call; result valid in all threads) -------------------
+template <int NW>
+__device__ __forceinline__ void block_reduce(double& sum, double& mx, double& mn, double (*red)[8]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(kFull, sum, o);
+    mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));
+    mn = fmin(mn, __shfl_xor_sync(kFull, mn, o));
+  }
+  if (NW == 1) return;
+  const int w = threadIdx.x >> 5;
+  __syncthreads();   // protect red[] from the previous use
+  if ((threadIdx.x & 31) == 0) { red[0][w] = sum; red[1][w] = mx; red[2][w] = mn; }
+  __syncthreads();
+  sum = red[0][0]; mx = red[1][0]; mn = red[2][0];
+#pragma unroll
+  for (int i = 1; i < NW; ++i) { sum += red[0][i]; mx = fmax(mx, red[1][i]); mn = fmin(mn, red[2][i]); }
+}
+
+__device__ __forceinline__ double quad_sum(double v) {   // sum over the 4 legs of a time step
+  v += __shfl_xor_sync(kFull, v, 1);
+  v += __shfl_xor_sync(kFull, v, 2);
+  return v;
+}
+
+// ---- in-place Cholesky of the packed SPD matrix, one thread per row (left-looking) ------------
+template <int H>
+__device__ __forceinline__ void cholesky_rows(Smem<H>& sm) {
+  constexpr int N6 = Cfg<H>::N6;
+  const int i = threadIdx.x;
+  double* row_i = sm.psi + tri(i < N6 ? i : 0, 0);
+  if (i == 0) sm.flag = 0;   // published by the first barrier below
+  for (int j = 0; j < N6; ++j) {
+    double v = 0.0;
+    if (i >= j && i < N6) {
+      const double* row_j = sm.psi + tri(j, 0);
+      double acc0 = row_i[j], acc1 = 0.0;
+      int k = 0;
+      for (; k + 1 < j; k += 2) {
+        acc0 = fma(-row_i[k], row_j[k], acc0);
+        acc1 = fma(-row_i[k + 1], row_j[k + 1], acc1);
+      }
+      if (k < j) acc0 = fma(-row_i[k], row_j[k], acc0);
+      v = acc0 + acc1;
+      if (i == j) {
+        if (!(v > 0.0)) { sm.flag = 1; v = 1e-300; }
+        const double d = sqrt(v);
+        row_i[j] = d;
+        sm.rdiag[j] = 1.0 / d;
+      }
+    }
+    __syncthreads();
+    if (i > j && i < N6) row_i[j] = v * sm.rdiag[j];
+    __syncthreads();
+  }
+}
+
+// ---- Psi x = b with the factor, b/x in sm.avec; executed by warp 0 only ----------------------
+template <int H>
+__device__ __forceinline__ void tri_solve_warp0(Smem<H>& sm) {
+  constexpr int N6 = Cfg<H>::N6;
+  constexpr int RPL = Cfg<H>::RPL;
+  const int lane = threadIdx.x;   // caller guarantees threadIdx.x < 32
+  double x[RPL];
+#pragma unroll
+  for (int r = 0; r < RPL; ++r) { const int i = lane + 32 * r; x[r] = i < N6 ? sm.avec[i] : 0.0; }
+  // forward: L y = b
+#pragma unroll
+  for (int slot = 0; slot < RPL; ++slot) {
+    for (int jj = 0; jj < 32; ++jj) {
+      const int j = slot * 32 + jj;
+      if (j >= N6) break;
+      double xj = x[slot] * sm.rdiag[j];
+      xj = __shfl_sync(kFull, xj, jj);
+      if (lane == jj) x[slot] = xj;
+#pragma unroll
+      for (int r = 0; r < RPL; ++r) {
+        const int i = lane + 32 * r;
+        if (i > j && i < N6) x[r] = fma(-sm.psi[tri(i, j)], xj, x[r]);
+      }
+    }
+  }
+  // backward: L^T x = y
+#pragma unroll
+  for (int slot = RPL - 1; slot >= 0; --slot) {
+    for (int jj = 31; jj >= 0; --jj) {
+      const int j = slot * 32 + jj;
+      if (j >= N6) continue;
+      double xj = x[slot] * sm.rdiag[j];
+      xj = __shfl_sync(kFull, xj, jj);
+      if (lane == jj) x[slot] = xj;
+      const double* row_j = sm.psi + tri(j, 0);
+#pragma unroll
+      for (int r = 0; r < RPL; ++r) {
+        const int i = lane + 32 * r;
+        if (i < j) x[r] = fma(-row_j[i], xj, x[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RPL; ++r) { const int i = lane + 32 * r; if (i < N6) sm.avec[i] = x[r]; }
+}
+
+// Psi := scale * K^-1 (packed), all threads
+template <int H>
+__device__ __forceinline__ void psi_init(Smem<H>& sm, double scale) {
+  constexpr int N6 = Cfg<H>::N6;
+  for (int p = threadIdx.x; p < N6; p += blockDim.x) {
+    const int j = p / 6, c = p - 6 * j;
+    double* row = sm.psi + tri(p, 0);
+    for (int q = 0; q <= p; ++q) {
+      const int k = q / 6, d = q - 6 * k;
+      double v = 0.0;
+      if (c < 3 && d < 3) {
+        const int a = 3 * j + c, b = 3 * k + d;   // a >= b because p >= q ... not always when j == k
+        v = a >= b ? sm.kinv_ang[tri(a, b)] : sm.kinv_ang[tri(b, a)];
+      } else if (c == d) {
+        v = sm.kinv_lin[c - 3][tri(j, k)];
+      }
+      row[q] = scale * v;
+    }
+  }
+}
+
+// ---- the per-block 3x3 part --------------------------------------------------------------------
+struct Block3 { double e00, e11, e22, e20, e21; };   // symmetric with e10 == 0; reused for E^-1
+
+// E = 2 alpha I + sum_r D_r g_r g_r^T  ->  E^-1 via a cancellation-free Cholesky.
+// g rows: (-1,0,mu0) (1,0,mu1) (0,-1,mu2) (0,1,mu3) (0,0,1).
+__device__ __forceinline__ void block_inverse(const double* dd, const double* mu, double two_alpha, double* einv) {
+  const double sx = dd[0] + dd[1] + two_alpha;
+  const double sy = dd[2] + dd[3] + two_alpha;
+  const double exz = -mu[0] * dd[0] + mu[1] * dd[1];
+  const double eyz = -mu[2] * dd[2] + mu[3] * dd[3];
+  // Schur complement of the z pivot, expanded so that every term is non-negative
+  const double ms = mu[0] + mu[1], mt = mu[2] + mu[3];
+  const double zz = two_alpha + dd[4] +
+                    (dd[0] * dd[1] * ms * ms + two_alpha * (mu[0] * mu[0] * dd[0] + mu[1] * mu[1] * dd[1])) / sx +
+                    (dd[2] * dd[3] * mt * mt + two_alpha * (mu[2] * mu[2] * dd[2] + mu[3] * mu[3] * dd[3])) / sy;
+  // L = [[sqrt(sx),0,0],[0,sqrt(sy),0],[exz/sqrt(sx), eyz/sqrt(sy), sqrt(zz)]]
+  // E^-1 = L^-T L^-1 with L^-1 = [[1/l00,0,0],[0,1/l11,0],[-l20/(l00 l22), -l21/(l11 l22), 1/l22]]
+  const double izz = 1.0 / zz;
+  const double ax = exz / sx, ay = eyz / sy;   // l20/l00, l21/l11
+  // einv packed as (xx, yy, zz, xz, yz, xy)
+  einv[0] = 1.0 / sx + ax * ax * izz;
+  einv[1] = 1.0 / sy + ay * ay * izz;
+  einv[2] = izz;
+  einv[3] = -ax * izz;
+  einv[4] = -ay * izz;
+  einv[5] = ax * ay * izz;
+}
+
+__device__ __forceinline__ void sym3_mul(const double* m, const double* v, double* o) {
+  // m packed as (xx, yy, zz, xz, yz, xy)
+  o[0] = m[0] * v[0] + m[5] * v[1] + m[3] * v[2];
+  o[1] = m[5] * v[0] + m[1] * v[1] + m[4] * v[2];
+  o[2] = m[3] * v[0] + m[4] * v[1] + m[2] * v[2];
+}
+
+// G^T w for the 10 rows (upper 0..4, lower 5..9 with negated normals)
+__device__ __forceinline__ void gt_mul(const double* w, const double* mu, double* o) {
+  const double e0 = w[0] - w[5], e1 = w[1] - w[6], e2 = w[2] - w[7], e3 = w[3] - w[8], e4 = w[4] - w[9];
+  o[0] = e1 - e0;
+  o[1] = e3 - e2;
+  o[2] = mu[0] * e0 + mu[1] * e1 + mu[2] * e2 + mu[3] * e3 + e4;
+}
+
+// c_r = g_r . f  (5 values)
+__device__ __forceinline__ void g_mul(const double* f, const double* mu, double* c) {
+  c[0] = -f[0] + mu[0] * f[2];
+  c[1] = f[0] + mu[1] * f[2];
+  c[2] = -f[1] + mu[2] * f[2];
+  c[3] = f[1] + mu[3] * f[2];
+  c[4] = f[2];
+}
+
+template <int H>
+__global__ void __launch_bounds__(Cfg<H>::NT)
+mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
+                 const float* __restrict__ g_com_vel, const float* __restrict__ g_rpy,
+                 const float* __restrict__ g_rpy_rate, const uint8_t* __restrict__ g_contacts,
+                 const float* __restrict__ g_feet, const float* __restrict__ g_cmd,
+                 const float* __restrict__ g_com_height, int zero_yaw,
+                 float* __restrict__ g_forces, float* __restrict__ g_hforces, int32_t* __restrict__ g_info) {
+  using C = Cfg<H>;
+  constexpr int N6 = C::N6;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<H>& sm = *reinterpret_cast<Smem<H>*>(smem_raw);
+
+  const int env = blockIdx.x;
+  if (env >= n_env) return;
+  const int tid = threadIdx.x;
+  const int t_blk = tid >> 2, leg = tid & 3;
+  const bool is_blk = tid < C::NB;
+
+  // ---------------------------------------------------------------- parameters (uniform loads)
+  const double dt = ws->dt, two_alpha = 2.0 * ws->alpha;
+  const double inv_mass = ws->inv_mass;
+  const double fzmax = ws->fz_max, fzmin = ws->fz_min;
+  double mu[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) mu[r] = ws->mu[r];
+  const double big_u = (mu[0] + 1.0) * fzmax;
+
+  // ---------------------------------------------------------------- per-env inputs
+  const unsigned contact_word = *reinterpret_cast<const unsigned*>(g_contacts + 4 * (size_t)env);
+  const bool stance_leg[4] = {(contact_word & 0xffu) != 0, (contact_word & 0xff00u) != 0,
+                              (contact_word & 0xff0000u) != 0, (contact_word & 0xff000000u) != 0};
+  const int n_stance = (int)stance_leg[0] + stance_leg[1] + stance_leg[2] + stance_leg[3];
+  const bool active_blk = is_blk && ((contact_word >> (8 * leg)) & 0xffu) != 0;
+
+  if (n_stance == 0) {   // every force pinned to zero by the bounds
+    for (int i = tid; i < 12; i += blockDim.x) g_forces[12 * (size_t)env + i] = 0.f;
+    if (g_hforces) for (int i = tid; i < 12 * H; i += blockDim.x) g_hforces[12 * H * (size_t)env + i] = 0.f;
+    if (g_info && tid < 4) g_info[4 * (size_t)env + tid] = tid == RG_INFO_STATUS ? (RG_STATUS_NO_STANCE | RG_STATUS_POLISHED) : 0;
+    return;
+  }
+
+  const double roll = g_rpy[3 * (size_t)env + 0], pitch = g_rpy[3 * (size_t)env + 1],
+               yaw = zero_yaw ? 0.0 : (double)g_rpy[3 * (size_t)env + 2];
+  double sr, cr, sp, cp, sy, cy;
+  sincos(roll, &sr, &cr);
+  sincos(pitch, &sp, &cp);
+  sincos(yaw, &sy, &cy);
+
+  // ---------------------------------------------------------------- setup (thread 0..; tiny)
+  if (tid == 0) sm.flag = 0;
+  // c2 table
+  for (int i = tid; i < H * H; i += blockDim.x) sm.c2tab[i] = c2f(H, i / H, i % H);
+
+  // T(rpy): angular velocity -> rpy rate;  K2_ang = 2 dt^4 T^T diag(w_rpy) T
+  const double tm[9] = {cy / cp, sy / cp, 0.0, -sy, cy, 0.0, cy * sp / cp, sy * sp / cp, 1.0};
+  const double dt2 = dt * dt, dt4 = dt2 * dt2;
+  if (tid < 9) {
+    const int c = tid / 3, d = tid % 3;
+    double v = 0.0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) v += ws->w_rho[r] * tm[3 * r + c] * tm[3 * r + d];
+    sm.k2ang[tid] = 2.0 * dt4 * v;
+  }
+  if (tid < 6) sm.k1[tid] = 2.0 * dt2 * ws->w_nu[tid];
+  if (tid < 3) sm.k2lin[tid] = 2.0 * dt4 * ws->w_rho[3 + tid];
+
+  // foot lever arms in the (yaw aligned) world frame: R = Rx Ry Rz (sic, see oracle/convex_mpc.py)
+  // R_body = Rz Ry Rx for the inertia
+  double com_z;
+  {
+    const double rf[9] = {cp * cy, -cp * sy, sp,
+                          sr * sp * cy + cr * sy, -sr * sp * sy + cr * cy, -sr * cp,
+                          -cr * sp * cy + sr * sy, cr * sp * sy + sr * cy, cr * cp};
+    double zsum = 0.0;
+    double fw[4][3];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float* fp = g_feet + 12 * (size_t)env + 3 * l;
+      const double px = fp[0], py = fp[1], pz = fp[2];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) fw[l][r] = rf[3 * r] * px + rf[3 * r + 1] * py + rf[3 * r + 2] * pz;
+      if (stance_leg[l]) zsum += fw[l][2];
+    }
+    com_z = g_com_height ? (double)g_com_height[env] : fabs(zsum / n_stance);
+    if (tid < 4) {
+      const double rb[9] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
+                            sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
+                            -sp, cp * sr, cp * cr};
+      // I_w^-1 = R I_b^-1 R^T
+      double tmp[9], iw[9];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          double v = 0.0;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) v += rb[3 * a + c] * ws->inv_inertia[3 * c + b];
+          tmp[3 * a + b] = v;
+        }
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          double v = 0.0;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) v += tmp[3 * a + c] * rb[3 * b + c];
+          iw[3 * a + b] = v;
+        }
+      const double rx = fw[tid][0], ry = fw[tid][1], rz = fw[tid][2];
+      const double sk[9] = {0.0, -rz, ry, rz, 0.0, -rx, -ry, rx, 0.0};
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          double v = 0.0;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) v += iw[3 * a + c] * sk[3 * c + b];
+          sm.bang[tid][3 * a + b] = v;
+        }
+    }
+  }
+  __syncthreads();
+
+  // Q_t = (K1 + gamma_t K2)^-1 : 3x3 SPD angular block (packed xx,yy,zz,xz,yz,xy) + 3 scalars
+  if (tid < H) {
+    const double gm = ws->eig_gamma[tid];
+    const double m00 = sm.k1[0] + gm * sm.k2ang[0], m11 = sm.k1[1] + gm * sm.k2ang[4], m22 = sm.k1[2] + gm * sm.k2ang[8];
+    const double m01 = gm * sm.k2ang[1], m02 = gm * sm.k2ang[2], m12 = gm * sm.k2ang[5];
+    const double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
+    const double det = m00 * c00 + m01 * c01 + m02 * c02;
+    const double id = 1.0 / det;
+    sm.qinv[tid][0] = c00 * id;
+    sm.qinv[tid][1] = (m00 * m22 - m02 * m02) * id;
+    sm.qinv[tid][2] = (m00 * m11 - m01 * m01) * id;
+    sm.qinv[tid][3] = c02 * id;                       // xz
+    sm.qinv[tid][4] = (m01 * m02 - m00 * m12) * id;   // yz
+    sm.qinv[tid][5] = c01 * id;                       // xy
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sm.qinv[tid][6 + c] = 1.0 / (sm.k1[3 + c] + gm * sm.k2lin[c]);
+  }
+  __syncthreads();
+
+  // K^-1 = (U (x) I) blkdiag(Q_t) (U^T (x) I)
+  for (int idx = tid; idx < C::NKA; idx += blockDim.x) {
+    // invert tri(): a = row, b = col
+    int a = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+    while (tri(a + 1, 0) <= idx) ++a;
+    while (tri(a, 0) > idx) --a;
+    const int b = idx - tri(a, 0);
+    const int j = a / 3, c = a % 3, k = b / 3, d = b % 3;
+    // packed index of the symmetric 3x3 (xx,yy,zz,xz,yz,xy)
+    const int lo = c < d ? c : d, hi = c < d ? d : c;
+    const int pk = (lo == hi) ? lo : (lo == 0 && hi == 2) ? 3 : (lo == 1 && hi == 2) ? 4 : 5;
+    double v = 0.0;
+    for (int t = 0; t < H; ++t) v = fma(ws->eig_u[j * H + t] * ws->eig_u[k * H + t], sm.qinv[t][pk], v);
+    sm.kinv_ang[idx] = v;
+  }
+  for (int idx = tid; idx < 3 * C::NKL; idx += blockDim.x) {
+    const int c = idx / C::NKL, r = idx % C::NKL;
+    int j = (int)((sqrt(8.0 * r + 1.0) - 1.0) * 0.5);
+    while (tri(j + 1, 0) <= r) ++j;
+    while (tri(j, 0) > r) --j;
+    const int k = r - tri(j, 0);
+    double v = 0.0;
+    for (int t = 0; t < H; ++t) v = fma(ws->eig_u[j * H + t] * ws->eig_u[k * H + t], sm.qinv[t][6 + c], v);
+    sm.kinv_lin[c][r] = v;
+  }
+
+  // g~_j = 2 sum_{i>j} [ dt L_nu e_nu(i) + dt^2 (i-j-1/2) G6^T L_rho e_rho(i) ]   (thread per (j,c))
+  {
+    const double wx = g_rpy_rate[3 * (size_t)env + 0], wy = g_rpy_rate[3 * (size_t)env + 1], wz = g_rpy_rate[3 * (size_t)env + 2];
+    const double vx = g_com_vel[3 * (size_t)env + 0], vy = g_com_vel[3 * (size_t)env + 1], vz = g_com_vel[3 * (size_t)env + 2];
+    const double dvx = g_cmd[3 * (size_t)env + 0], dvy = g_cmd[3 * (size_t)env + 1], dwz = g_cmd[3 * (size_t)env + 2];
+    const double grav = -ws->gravity;
+    // rpy rate at t0:  T w
+    const double rr0 = tm[0] * wx + tm[1] * wy + tm[2] * wz;
+    const double rr1 = tm[3] * wx + tm[4] * wy + tm[5] * wz;
+    const double rr2 = tm[6] * wx + tm[7] * wy + tm[8] * wz;
+    if (tid < N6) {
+      const int j = tid / 6, c = tid % 6;
+      double acc = 0.0;
+      for (int i = j + 1; i <= H; ++i) {
+        const double ti = i * dt;
+        // errors of the free response against the reference trajectory
+        const double er0 = roll + ti * rr0 - 0.0;
+        const double er1 = pitch + ti * rr1 - 0.0;
+        const double er2 = yaw + ti * rr2 - (yaw + ti * dwz);
+        const double ep0 = 0.0 + ti * vx - ti * dvx;
+        const double ep1 = 0.0 + ti * vy - ti * dvy;
+        const double ep2 = com_z + ti * vz + 0.5 * ti * ti * grav - ws->height;
+        const double en[6] = {wx - 0.0, wy - 0.0, wz - dwz, vx - dvx, vy - dvy, vz + ti * grav - 0.0};
+        const double lr0 = ws->w_rho[0] * er0, lr1 = ws->w_rho[1] * er1, lr2 = ws->w_rho[2] * er2;
+        double rho_term;
+        if (c < 3) rho_term = tm[c] * lr0 + tm[3 + c] * lr1 + tm[6 + c] * lr2;          // (T^T L e)_c
+        else rho_term = ws->w_rho[c] * (c == 3 ? ep0 : c == 4 ? ep1 : ep2);
+        acc += 2.0 * (dt * ws->w_nu[c] * en[c] + dt2 * (i - j - 0.5) * rho_term);
+      }
+      sm.gt[tid] = acc;
+    }
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- per-block constants
+  double ba[9];   // A_leg
+#pragma unroll
+  for (int i = 0; i < 9; ++i) ba[i] = active_blk ? sm.bang[leg][i] : 0.0;
+  double q[3] = {0.0, 0.0, 0.0};
+  if (active_blk) {
+    const double* g6 = sm.gt + 6 * t_blk;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) q[d] = ba[d] * g6[0] + ba[3 + d] * g6[1] + ba[6 + d] * g6[2] + inv_mass * g6[3 + d];
+  }
+
+  // upper bounds hv (rows 0..4) and lower bounds (rows 5..9 as -g.f <= -l)
+  const double hv_up[5] = {big_u, big_u, big_u, big_u, fzmax};
+  const double lo_b[5] = {0.0, 0.0, 0.0, 0.0, fzmin};
+
+  // P u for the force triple held by this thread (all threads must call)
+  auto apply_p = [&](const double* uu, double* out) {
+    double a6[6];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      a6[c] = ba[3 * c] * uu[0] + ba[3 * c + 1] * uu[1] + ba[3 * c + 2] * uu[2];
+      a6[3 + c] = inv_mass * uu[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      a6[c] = quad_sum(active_blk ? a6[c] : 0.0);
+    }
+    if (is_blk && leg == 0) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) sm.avec[6 * t_blk + c] = a6[c];
+    }
+    __syncthreads();
+    if (tid < N6) {
+      const int j = tid / 6, c = tid % 6;
+      double s1 = 0.0;
+      for (int k = 0; k < H; ++k) s1 = fma(c1f(H, j, k), sm.avec[6 * k + c], s1);
+      double val = sm.k1[c] * s1;
+      if (c < 3) {
+        double s20 = 0.0, s21 = 0.0, s22 = 0.0;
+        for (int k = 0; k < H; ++k) {
+          const double cc = sm.c2tab[j * H + k];
+          s20 = fma(cc, sm.avec[6 * k + 0], s20);
+          s21 = fma(cc, sm.avec[6 * k + 1], s21);
+          s22 = fma(cc, sm.avec[6 * k + 2], s22);
+        }
+        val += sm.k2ang[3 * c] * s20 + sm.k2ang[3 * c + 1] * s21 + sm.k2ang[3 * c + 2] * s22;
+      } else {
+        double s2 = 0.0;
+        for (int k = 0; k < H; ++k) s2 = fma(sm.c2tab[j * H + k], sm.avec[6 * k + c], s2);
+        val += sm.k2lin[c - 3] * s2;
+      }
+      sm.kvec[tid] = val;
+    }
+    __syncthreads();
+    if (active_blk) {
+      const double* kv = sm.kvec + 6 * t_blk;
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        out[d] = two_alpha * uu[d] + ba[d] * kv[0] + ba[3 + d] * kv[1] + ba[6 + d] * kv[2] + inv_mass * kv[3 + d];
+    } else {
+      out[0] = out[1] = out[2] = 0.0;
+    }
+  };
+
+  // Adds sum_legs (B M B^T) to the diagonal 6x6 blocks of Psi, M symmetric 3x3 packed
+  // (xx,yy,zz,xz,yz,xy); all threads call (shuffles), leg-0 lanes write.
+  auto add_n_blocks = [&](const double* m) {
+    // AM = A M  (3x3), N_aa = AM A^T (sym), N_al = AM / m, N_ll = M / m^2
+    double am[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double a0 = ba[3 * a], a1 = ba[3 * a + 1], a2 = ba[3 * a + 2];
+      am[3 * a + 0] = a0 * m[0] + a1 * m[5] + a2 * m[3];
+      am[3 * a + 1] = a0 * m[5] + a1 * m[1] + a2 * m[4];
+      am[3 * a + 2] = a0 * m[3] + a1 * m[4] + a2 * m[2];
+    }
+    double n[21];   // lower triangle of the 6x6 block, row-major: (r,c) -> r(r+1)/2 + c
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c <= r; ++c)
+        n[r * (r + 1) / 2 + c] = am[3 * r] * ba[3 * c] + am[3 * r + 1] * ba[3 * c + 1] + am[3 * r + 2] * ba[3 * c + 2];
+    const double mfull[9] = {m[0], m[5], m[3], m[5], m[1], m[4], m[3], m[4], m[2]};
+#pragma unroll
+    for (int r = 3; r < 6; ++r) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) n[r * (r + 1) / 2 + c] = am[3 * c + (r - 3)] * inv_mass;   // N_la = (AM)^T / m
+#pragma unroll
+      for (int c = 3; c <= r; ++c) n[r * (r + 1) / 2 + c] = mfull[3 * (r - 3) + (c - 3)] * inv_mass * inv_mass;
+    }
+#pragma unroll
+    for (int i = 0; i < 21; ++i) n[i] = quad_sum(active_blk ? n[i] : 0.0);
+    if (is_blk && leg == 0) {
+      const int base = 6 * t_blk;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) sm.psi[tri(base + r, base + c)] += n[r * (r + 1) / 2 + c];
+    }
+  };
+
+  // Woodbury solve of (E + W^T K W) x = b given E^-1 blocks (einv) and the factor of Psi.
+  // All threads call.
+  auto woodbury = [&](const double* einv, const double* b, double* x) {
+    double w[3];
+    sym3_mul(einv, b, w);   // E^-1 b
+    double t6[6];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      t6[c] = ba[3 * c] * w[0] + ba[3 * c + 1] * w[1] + ba[3 * c + 2] * w[2];
+      t6[3 + c] = inv_mass * w[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) t6[c] = quad_sum(active_blk ? t6[c] : 0.0);
+    if (is_blk && leg == 0) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) sm.avec[6 * t_blk + c] = t6[c];
+    }
+    __syncthreads();
+    if (tid < 32) tri_solve_warp0<H>(sm);
+    __syncthreads();
+    if (active_blk) {
+      const double* v = sm.avec + 6 * t_blk;
+      double bv[3], ebv[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) bv[d] = ba[d] * v[0] + ba[3 + d] * v[1] + ba[6 + d] * v[2] + inv_mass * v[3 + d];
+      sym3_mul(einv, bv, ebv);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) x[d] = w[d] - ebv[d];
+    } else {
+      x[0] = x[1] = x[2] = 0.0;
+    }
+    __syncthreads();   // avec is reused by the next caller
+  };
+
+  // ---------------------------------------------------------------- interior point
+  double u[3] = {0.0, 0.0, 0.0}, s[10], lam[10];
+  const double fz0 = sqrt(fmax(fzmin, 1e-3 * fzmax) * fzmax);
+  u[2] = active_blk ? fz0 : 0.0;
+  double qmax = active_blk ? fmax(fabs(q[0]), fmax(fabs(q[1]), fabs(q[2]))) : 0.0;
+  {
+    double dsum = 0.0, dmn = 0.0;
+    block_reduce<C::NW>(dsum, qmax, dmn, sm.red);
+  }
+  const double qscale = fmax(1.0, qmax);
+  {
+    double c5[5];
+    g_mul(u, mu, c5);
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      s[r] = hv_up[r] - c5[r];
+      s[5 + r] = c5[r] - lo_b[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      if (!active_blk) s[r] = 1.0;
+      lam[r] = active_blk ? 0.1 * qscale / s[r] : 0.0;
+    }
+  }
+  const double m_total = 10.0 * H * n_stance;
+  const int max_iters = ws->max_ipm_iters;
+  const int max_polish = ws->max_polish_rounds;
+  double tol = ws->ipm_tol;
+  int iters = 0, polish_rounds = 0, status = 0, n_active_out = 0;
+  double u_out[3] = {u[0], u[1], u[2]};
+
+  // Escalation ladder: interior point to `tol`, then the active-set polish; if the polish does not
+  // verify within its round budget (weakly active constraints: multipliers of order alpha), drive
+  // the interior point 100x further and try again.  Last resort: the best interior-point iterate.
+  double best_res = 1e300, prev_res = 1e300;
+  double u_best[3] = {u[0], u[1], u[2]};
+  int stall = 0;
+  bool done = false;
+  for (int attempt = 0; attempt < 4 && !done; ++attempt) {
+    bool converged = false, ipm_dead = false;
+    while (true) {
+      double pu[3], rd[3], gl[3];
+      apply_p(u, pu);
+      gt_mul(lam, mu, gl);
+      double sl = 0.0, rdmax = 0.0, dmn = 0.0;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { rd[d] = pu[d] + q[d] + gl[d]; rdmax = fmax(rdmax, fabs(rd[d])); }
+#pragma unroll
+      for (int r = 0; r < 10; ++r) sl += s[r] * lam[r];
+      if (!active_blk) { sl = 0.0; rdmax = 0.0; }
+      block_reduce<C::NW>(sl, rdmax, dmn, sm.red);
+      const double mu_c = sl / m_total;
+      const double res = fmax(rdmax, mu_c) / qscale;
+      if (res < best_res) {
+        best_res = res;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) u_best[d] = u[d];
+      }
+      if (res < tol) { converged = true; break; }
+      stall = (res > 0.9 * prev_res) ? stall + 1 : 0;
+      prev_res = res;
+      if (iters >= max_iters || stall >= 3 || !(res == res)) { ipm_dead = true; break; }
+      ++iters;
+
+      // block 3x3 parts and Psi
+      double dd[5], einv[6];
+#pragma unroll
+      for (int r = 0; r < 5; ++r) dd[r] = lam[r] / s[r] + lam[5 + r] / s[5 + r];
+      block_inverse(dd, mu, two_alpha, einv);
+      psi_init<H>(sm, 1.0);
+      __syncthreads();
+      add_n_blocks(einv);
+      __syncthreads();
+      cholesky_rows<H>(sm);
+      if (sm.flag) { status |= RG_STATUS_NUMERIC; ipm_dead = true; break; }
+
+      // predictor: r_c = s lam  ->  rhs = -(P u + q)
+      double rhs[3], dxa[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) rhs[d] = -(pu[d] + q[d]);
+      woodbury(einv, rhs, dxa);
+      double c5[5], pa[10];
+      g_mul(dxa, mu, c5);
+      double amax = 1.0;   // largest feasible affine step
+      double dsum = 0.0, dmx = 0.0;
+#pragma unroll
+      for (int r = 0; r < 10; ++r) {
+        const double ds = r < 5 ? -c5[r] : c5[r - 5];
+        const double dl = -lam[r] - lam[r] * ds / s[r];
+        pa[r] = ds * dl;
+        if (active_blk) {
+          if (ds < 0.0) amax = fmin(amax, -s[r] / ds);
+          if (dl < 0.0) amax = fmin(amax, -lam[r] / dl);
+        }
+      }
+      block_reduce<C::NW>(dsum, dmx, amax, sm.red);
+      double mu_aff = 0.0;
+#pragma unroll
+      for (int r = 0; r < 10; ++r) {
+        const double ds = r < 5 ? -c5[r] : c5[r - 5];
+        const double dl = -lam[r] - lam[r] * ds / s[r];
+        mu_aff += (s[r] + amax * ds) * (lam[r] + amax * dl);
+      }
+      if (!active_blk) mu_aff = 0.0;
+      {
+        double dmx2 = 0.0, dmn2 = 0.0;
+        block_reduce<C::NW>(mu_aff, dmx2, dmn2, sm.red);
+      }
+      mu_aff /= m_total;
+      const double sig = (mu_aff / mu_c) * (mu_aff / mu_c) * (mu_aff / mu_c);
+      const double sigmu = sig * mu_c;
+
+      // corrector: r_c = s lam + ds_a dl_a - sigma mu ; rhs = -rd + G^T (r_c / s)
+      double wv[10], gw[3], dx[3];
+#pragma unroll
+      for (int r = 0; r < 10; ++r) wv[r] = (s[r] * lam[r] + pa[r] - sigmu) / s[r];
+      gt_mul(wv, mu, gw);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) rhs[d] = -rd[d] + gw[d];
+      woodbury(einv, rhs, dx);
+      g_mul(dx, mu, c5);
+      double step = 1e30;
+#pragma unroll
+      for (int r = 0; r < 10; ++r) {
+        const double ds = r < 5 ? -c5[r] : c5[r - 5];
+        const double dl = (-(s[r] * lam[r] + pa[r] - sigmu) - lam[r] * ds) / s[r];
+        if (active_blk) {
+          if (ds < 0.0) step = fmin(step, -s[r] / ds);
+          if (dl < 0.0) step = fmin(step, -lam[r] / dl);
+        }
+      }
+      block_reduce<C::NW>(dsum, dmx, step, sm.red);
+      step = fmin(1.0, 0.99 * step);
+#pragma unroll
+      for (int r = 0; r < 10; ++r) {
+        const double ds = r < 5 ? -c5[r] : c5[r - 5];
+        const double dl = (-(s[r] * lam[r] + pa[r] - sigmu) - lam[r] * ds) / s[r];
+        if (active_blk) {
+          s[r] += step * ds;
+          lam[r] += step * dl;
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) u[d] += step * dx[d];
+    }
+    if (converged) status |= RG_STATUS_IPM_CONVERGED; else status &= ~RG_STATUS_IPM_CONVERGED;
+    if (max_polish <= 0) {
+      if (ipm_dead || tol <= 1e-12) break;
+      tol = 1e-12;       // without the polish the interior point itself has to resolve the alpha-directions
+      continue;
+    }
+
+    // -------------------------------------------------------------- active-set polish
+    unsigned act = 0;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) if (active_blk && lam[r] > s[r]) act |= 1u << r;
+    bool polished = false;
+    double up[3] = {0.0, 0.0, 0.0};
+    for (int round = 0; round < max_polish; ++round) {
+      ++polish_rounds;
+      // --- per block: orthonormal basis of the active normals (<= 3), null-space basis Z, u0
+      double e[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      double rr[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};   // a_i = sum_k rr[k][i] e_k
+      double bt[3] = {0, 0, 0};
+      int rows[3] = {-1, -1, -1};
+      int na = 0;
+      if (active_blk) {
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+          if (!((act >> r) & 1u) || na >= 3) continue;
+          const int rw = r < 5 ? r : r - 5;
+          double a[3] = {rw == 0 ? -1.0 : rw == 1 ? 1.0 : 0.0, rw == 2 ? -1.0 : rw == 3 ? 1.0 : 0.0,
+                         rw < 4 ? mu[rw] : 1.0};
+          const double target = r < 5 ? hv_up[rw] : lo_b[rw];
+          double coef[3] = {0, 0, 0};
+          for (int k = 0; k < na; ++k) {
+            coef[k] = a[0] * e[k][0] + a[1] * e[k][1] + a[2] * e[k][2];
+            a[0] -= coef[k] * e[k][0]; a[1] -= coef[k] * e[k][1]; a[2] -= coef[k] * e[k][2];
+          }
+          const double nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+          if (nrm < 1e-9) { act &= ~(1u << r); continue; }   // dependent normal: drop
+          e[na][0] = a[0] / nrm; e[na][1] = a[1] / nrm; e[na][2] = a[2] / nrm;
+          for (int k = 0; k < na; ++k) rr[k][na] = coef[k];
+          rr[na][na] = nrm;
+          bt[na] = target;
+          rows[na] = r;
+          ++na;
+        }
+        // rows beyond the third independent one cannot be held: drop them from the guess
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+          if (((act >> r) & 1u) && r != rows[0] && r != rows[1] && r != rows[2]) act &= ~(1u << r);
+        }
+      }
+      // particular solution u0 = sum_k c_k e_k with a_i . u0 = b_i
+      double cpar[3] = {0, 0, 0};
+      for (int i = 0; i < na; ++i) {
+        double v = bt[i];
+        for (int k = 0; k < i; ++k) v -= rr[k][i] * cpar[k];
+        cpar[i] = v / rr[i][i];
+      }
+      double u0[3] = {0, 0, 0};
+      for (int k = 0; k < na; ++k) { u0[0] += cpar[k] * e[k][0]; u0[1] += cpar[k] * e[k][1]; u0[2] += cpar[k] * e[k][2]; }
+      // null-space basis z[0..nf)
+      double z[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      const int nf = active_blk ? 3 - na : 0;
+      if (active_blk) {
+        if (na == 0) { z[0][0] = 1.0; z[1][1] = 1.0; z[2][2] = 1.0; }
+        else if (na == 1) {
+          // two unit vectors orthogonal to e[0]
+          const double ax = fabs(e[0][0]), ay = fabs(e[0][1]), az = fabs(e[0][2]);
+          double h3[3] = {0, 0, 0};
+          if (ax <= ay && ax <= az) h3[0] = 1.0; else if (ay <= az) h3[1] = 1.0; else h3[2] = 1.0;
+          double v0 = e[0][1] * h3[2] - e[0][2] * h3[1], v1 = e[0][2] * h3[0] - e[0][0] * h3[2], v2 = e[0][0] * h3[1] - e[0][1] * h3[0];
+          const double n1 = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+          z[0][0] = v0 / n1; z[0][1] = v1 / n1; z[0][2] = v2 / n1;
+          z[1][0] = e[0][1] * z[0][2] - e[0][2] * z[0][1];
+          z[1][1] = e[0][2] * z[0][0] - e[0][0] * z[0][2];
+          z[1][2] = e[0][0] * z[0][1] - e[0][1] * z[0][0];
+        } else if (na == 2) {
+          z[0][0] = e[0][1] * e[1][2] - e[0][2] * e[1][1];
+          z[0][1] = e[0][2] * e[1][0] - e[0][0] * e[1][2];
+          z[0][2] = e[0][0] * e[1][1] - e[0][1] * e[1][0];
+        }
+      }
+      // M = Z Z^T (projector onto the free directions), packed (xx,yy,zz,xz,yz,xy)
+      double mproj[6] = {0, 0, 0, 0, 0, 0};
+      for (int k = 0; k < nf; ++k) {
+        mproj[0] += z[k][0] * z[k][0]; mproj[1] += z[k][1] * z[k][1]; mproj[2] += z[k][2] * z[k][2];
+        mproj[3] += z[k][0] * z[k][2]; mproj[4] += z[k][1] * z[k][2]; mproj[5] += z[k][0] * z[k][1];
+      }
+      // Psi_p = 2 alpha K^-1 + sum (B Z)(B Z)^T
+      psi_init<H>(sm, two_alpha);
+      __syncthreads();
+      add_n_blocks(mproj);
+      __syncthreads();
+      cholesky_rows<H>(sm);
+      if (sm.flag) { status |= RG_STATUS_NUMERIC; ipm_dead = true; break; }
+
+      // two passes: the solve and one step of iterative refinement
+#pragma unroll
+      for (int d = 0; d < 3; ++d) up[d] = u0[d];
+      for (int pass = 0; pass < 2; ++pass) {
+        double pu[3], gr[3];
+        apply_p(up, pu);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) gr[d] = pu[d] + q[d];
+        // projected gradient r = Z Z^T gr ; x = -(1/2a) [ r - Z Z^T B^T Psi_p^-1 B r ]
+        // = woodbury with "E^-1" := Z Z^T / (2 alpha) ... expressed through the projector:
+        double rproj[3], dx[3];
+        sym3_mul(mproj, gr, rproj);
+        // reuse woodbury(): E^-1 = mproj/(2a)  =>  Psi = K^-1 + B mproj B^T / (2a); we factorised
+        // 2a K^-1 + B mproj B^T = 2a * that, so scale the right-hand side instead.
+        double w[3] = {rproj[0], rproj[1], rproj[2]};
+        double t6[6];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          t6[c] = ba[3 * c] * w[0] + ba[3 * c + 1] * w[1] + ba[3 * c + 2] * w[2];
+          t6[3 + c] = inv_mass * w[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) t6[c] = quad_sum(active_blk ? t6[c] : 0.0);
+        if (is_blk && leg == 0) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) sm.avec[6 * t_blk + c] = t6[c];
+        }
+        __syncthreads();
+        if (tid < 32) tri_solve_warp0<H>(sm);
+        __syncthreads();
+        if (active_blk) {
+          const double* v = sm.avec + 6 * t_blk;
+          double bv[3], pbv[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) bv[d] = ba[d] * v[0] + ba[3 + d] * v[1] + ba[6 + d] * v[2] + inv_mass * v[3 + d];
+          sym3_mul(mproj, bv, pbv);
+#pragma unroll
+          for (int d = 0; d < 3; ++d) dx[d] = -(rproj[d] - pbv[d]) / two_alpha;
+        } else {
+          dx[0] = dx[1] = dx[2] = 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < 3; ++d) up[d] += dx[d];
+      }
+
+      // --- verify: primal feasibility of the rows left out, multiplier signs of the rows held
+      double pu[3], gr[3];
+      apply_p(up, pu);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) gr[d] = pu[d] + q[d];
+      unsigned act_new = act;
+      if (active_blk) {
+        double c5[5];
+        g_mul(up, mu, c5);
+        const double ftol = 1e-9 * fzmax;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+          const double slack = r < 5 ? hv_up[r] - c5[r] : c5[r - 5] - lo_b[r - 5];
+          if (!((act >> r) & 1u) && slack < -ftol) act_new |= 1u << r;
+        }
+        // multipliers: sum_i y_i a_i = -gr on span(e)
+        double y[3] = {0, 0, 0};
+        for (int i = na - 1; i >= 0; --i) {
+          double v = -(gr[0] * e[i][0] + gr[1] * e[i][1] + gr[2] * e[i][2]);
+          for (int k = i + 1; k < na; ++k) v -= rr[i][k] * y[k];
+          y[i] = v / rr[i][i];
+        }
+        for (int i = 0; i < na; ++i) {
+          // upper-bound rows need y >= 0, lower-bound rows y <= 0
+          const double ysgn = rows[i] < 5 ? y[i] : -y[i];
+          if (ysgn < -1e-10 * qscale) act_new &= ~(1u << rows[i]);
+        }
+      }
+      double changed = (act_new != act) ? 1.0 : 0.0, dmx = 0.0, dmn = 0.0;
+      block_reduce<C::NW>(changed, dmx, dmn, sm.red);
+      act = act_new;
+      if (changed == 0.0) { polished = true; break; }
+    }
+    if (polished) {
+      status |= RG_STATUS_POLISHED;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) u_out[d] = up[d];
+      double cnt = (double)__popc(act), dmx = 0.0, dmn = 0.0;
+      block_reduce<C::NW>(cnt, dmx, dmn, sm.red);
+      n_active_out = (int)cnt;
+      done = true;
+      break;
+    }
+    if (ipm_dead) break;
+    tol = fmax(tol * 1e-2, 1e-13);
+  }
+  if (!done) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) u_out[d] = u_best[d];
+  }
+
+  // ---------------------------------------------------------------- outputs (negated solution)
+  if (is_blk) {
+    const float fx = active_blk ? (float)(-u_out[0]) : 0.f;
+    const float fy = active_blk ? (float)(-u_out[1]) : 0.f;
+    const float fz = active_blk ? (float)(-u_out[2]) : 0.f;
+    if (t_blk == 0) {
+      float* o = g_forces + 12 * (size_t)env + 3 * leg;
+      o[0] = fx; o[1] = fy; o[2] = fz;
+    }
+    if (g_hforces) {
+      float* o = g_hforces + 12 * H * (size_t)env + 12 * t_blk + 3 * leg;
+      o[0] = fx; o[1] = fy; o[2] = fz;
+    }
+  }
+  if (g_info && tid == 0) {
+    int32_t* o = g_info + 4 * (size_t)env;
+    o[RG_INFO_IPM_ITERS] = iters;
+    o[RG_INFO_POLISH_ROUNDS] = polish_rounds;
+    o[RG_INFO_STATUS] = status;
+    o[RG_INFO_NUM_ACTIVE] = n_active_out;
+  }
+}
+
+template <int H>
+int launch_h(const RgMpcDev* ws, int n_env, const float* com_vel, const float* rpy, const float* rpy_rate,
+             const uint8_t* contacts, const float* feet, const float* command, const float* com_height,
+             int zero_yaw, float* forces, float* horizon_forces, int32_t* info, cudaStream_t stream) {
+  const size_t smem = sizeof(Smem<H>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(mpc_solve_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return rg_check_cuda(e, "cudaFuncSetAttribute(mpc_solve_kernel)");
+    attr_set = true;
+  }
+  mpc_solve_kernel<H><<<n_env, Cfg<H>::NT, smem, stream>>>(ws, n_env, com_vel, rpy, rpy_rate, contacts, feet, command,
+                                                            com_height, zero_yaw, forces, horizon_forces, info);
+  rg_count_launch();
+  return rg_check_cuda(cudaGetLastError(), "mpc_solve_kernel launch");
+}
+
+}  // namespace
+
+int rg_launch_mpc(const RgMpcDev* ws, int horizon, int n_env, const float* com_vel, const float* rpy,
+                  const float* rpy_rate, const uint8_t* contacts, const float* feet, const float* command,
+                  const float* com_height, int zero_yaw, float* forces, float* horizon_forces, int32_t* info,
+                  cudaStream_t stream) {
+  switch (horizon) {
+    case 5: return launch_h<5>(ws, n_env, com_vel, rpy, rpy_rate, contacts, feet, command, com_height, zero_yaw, forces, horizon_forces, info, stream);
+    case 10: return launch_h<10>(ws, n_env, com_vel, rpy, rpy_rate, contacts, feet, command, com_height, zero_yaw, forces, horizon_forces, info, stream);
+    case 20: return launch_h<20>(ws, n_env, com_vel, rpy, rpy_rate, contacts, feet, command, com_height, zero_yaw, forces, horizon_forces, info, stream);
+    default:
+      rg_set_error("unsupported horizon %d (kernels are built for 5, 10, 20)", horizon);
+      return RG_ERR_UNSUPPORTED;
+  }
+}

@@ -1,0 +1,239 @@
+"""ctypes binding of ``librg_cuda.so`` (C ABI: include/rg_cuda.h) for PyTorch tensors.
+
+PyTorch is plumbing here: it owns device memory and streams; every compute call goes through the
+C ABI with raw device pointers.  There is NO CPU fallback: loading fails loudly when the library
+is missing, and every wrapper refuses non-CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_size_t, c_uint64, c_void_p
+
+from . import build as _build
+
+RG_NUM_LEGS = 4
+RG_NUM_MOTORS = 12
+RG_ACTION_DIM = 60
+RG_MAX_HORIZON = 20
+RG_VEL_WINDOW_MAX = 64
+
+RG_LEG_SWING, RG_LEG_STANCE, RG_LEG_EARLY_CONTACT, RG_LEG_LOSE_CONTACT = 0, 1, 2, 3
+RG_INFO_IPM_ITERS, RG_INFO_POLISH_ROUNDS, RG_INFO_STATUS, RG_INFO_NUM_ACTIVE = 0, 1, 2, 3
+RG_STATUS_POLISHED, RG_STATUS_IPM_CONVERGED, RG_STATUS_NO_STANCE, RG_STATUS_NUMERIC = 1, 2, 4, 8
+
+# every symbol include/rg_cuda.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = (
+    "rg_mpc_default_params", "rg_workspace_bytes", "rg_mpc_setup", "rg_mpc_build_solve",
+    "rg_robot_calibrate_ik", "rg_robot_workspace_bytes", "rg_robot_setup",
+    "rg_gait_step", "rg_com_velocity_update", "rg_swing_targets", "rg_leg_ik", "rg_leg_fk",
+    "rg_force_to_torque", "rg_pack_hybrid_action", "rg_control_step", "rg_hybrid_motor_torque",
+    "rg_launch_count", "rg_last_error", "rg_version",
+)
+
+
+class MpcParams(Structure):
+    """``rg_mpc_params``."""
+    _fields_ = [
+        ("mass", c_double), ("inertia", c_double * 9), ("num_legs", c_int32), ("horizon", c_int32),
+        ("dt", c_double), ("weights", c_double * 13), ("alpha", c_double),
+        ("friction_coeffs", c_double * 4), ("gravity", c_double), ("fz_max", c_double),
+        ("fz_min", c_double), ("desired_body_height", c_double), ("ipm_tol", c_double),
+        ("max_ipm_iters", c_int32), ("max_polish_rounds", c_int32),
+    ]
+
+
+class LegChain(Structure):
+    """``rg_leg_chain``."""
+    _fields_ = [
+        ("p", (c_double * 3) * 3), ("r", (c_double * 9) * 3), ("axis", (c_double * 3) * 3),
+        ("toe", c_double * 3), ("ik_sign_hip", c_double), ("ik_sign_knee", c_double),
+    ]
+
+
+class RobotParams(Structure):
+    """``rg_robot_params``."""
+    _fields_ = [
+        ("legs", LegChain * 4), ("hip_positions", (c_double * 3) * 4),
+        ("motor_offset", c_double * 12), ("motor_direction", c_double * 12),
+        ("motor_kp", c_double * 12), ("motor_kd", c_double * 12),
+        ("stance_duration", c_double * 4), ("duty_factor", c_double * 4),
+        ("initial_leg_phase", c_double * 4), ("initial_leg_state", c_int32 * 4),
+        ("contact_detection_phase_threshold", c_double),
+        ("desired_height", c_double), ("foot_clearance", c_double), ("swing_kp", c_double * 3),
+        ("swing_max_clearance", c_double), ("velocity_window", c_int32),
+    ]
+
+
+class ControllerState(Structure):
+    """``rg_controller_state`` (all device pointers)."""
+    _fields_ = [(name, c_void_p) for name in (
+        "time_since_reset", "foot_contacts", "base_velocity_world", "base_orientation_xyzw", "base_rpy",
+        "base_rpy_rate", "foot_positions_base", "motor_angles", "command",
+        "vel_window", "vel_window_sum", "vel_window_corr", "vel_window_count", "vel_window_head",
+        "last_leg_state", "phase_switch_foot_local_position", "swing_joint_angles", "swing_joint_valid",
+        "desired_leg_state", "leg_state", "normalized_phase", "mpc_contact_state", "swing_foot_target",
+        "com_velocity_body", "contact_forces", "motor_torques", "solve_info", "action")]
+
+
+class RgCudaError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"rg_cuda error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = False):
+    """Load librg_cuda.so.  Raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        if build_if_missing:
+            _build.build()
+        else:
+            raise RuntimeError(
+                f"{path} is missing: build it with `python -m robot_gym.cuda.build` "
+                "(or __graft_entry__.build()). There is no CPU fallback for the controller kernels.")
+    lib = ctypes.CDLL(path)
+    lib.rg_last_error.restype = c_char_p
+    lib.rg_version.restype = c_char_p
+    lib.rg_launch_count.restype = c_uint64
+    lib.rg_mpc_default_params.argtypes = [POINTER(MpcParams), c_double, POINTER(c_double), c_double, c_int]
+    lib.rg_workspace_bytes.argtypes = [c_int, c_int, c_int, POINTER(c_size_t)]
+    lib.rg_mpc_setup.argtypes = [POINTER(MpcParams), c_void_p, c_size_t, c_void_p]
+    lib.rg_mpc_build_solve.argtypes = [c_void_p, c_int] + [c_void_p] * 10 + [c_void_p]
+    lib.rg_robot_calibrate_ik.argtypes = [POINTER(RobotParams), POINTER(c_double)]
+    lib.rg_robot_workspace_bytes.argtypes = [POINTER(c_size_t)]
+    lib.rg_robot_setup.argtypes = [POINTER(RobotParams), c_void_p, c_size_t, c_void_p]
+    lib.rg_gait_step.argtypes = [c_void_p, c_int] + [c_void_p] * 5 + [c_void_p]
+    lib.rg_com_velocity_update.argtypes = [c_void_p, c_int] + [c_void_p] * 9 + [c_void_p]
+    lib.rg_swing_targets.argtypes = [c_void_p, c_int] + [c_void_p] * 10 + [c_void_p]
+    lib.rg_leg_ik.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.rg_leg_fk.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    lib.rg_force_to_torque.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.rg_pack_hybrid_action.argtypes = [c_void_p, c_int] + [c_void_p] * 5 + [c_void_p]
+    lib.rg_control_step.argtypes = [c_void_p, c_void_p, c_int, POINTER(ControllerState), c_void_p]
+    lib.rg_hybrid_motor_torque.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(lib, name)
+        if name not in ("rg_last_error", "rg_version", "rg_launch_count"):
+            fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def check(code: int):
+    if code != 0:
+        raise RgCudaError(code, load().rg_last_error().decode())
+
+
+def launch_count() -> int:
+    return int(load().rg_launch_count())
+
+
+# ------------------------------------------------------------------------------------------ tensors
+def _ptr(t, dtype, shape_tail=None, allow_none=False):
+    """Device pointer of a contiguous CUDA tensor after dtype/shape checks."""
+    import torch
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError("tensor argument is None")
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("rg_cuda wrappers take CUDA tensors only (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    if shape_tail is not None and tuple(t.shape[1:]) != tuple(shape_tail):
+        raise ValueError(f"expected shape [N,{','.join(map(str, shape_tail))}], got {tuple(t.shape)}")
+    return c_void_p(t.data_ptr())
+
+
+def current_stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def default_mpc_params(mass, inertia9, desired_body_height, horizon=10) -> MpcParams:
+    p = MpcParams()
+    arr = (c_double * 9)(*[float(v) for v in inertia9])
+    check(load().rg_mpc_default_params(ctypes.byref(p), float(mass), arr, float(desired_body_height), int(horizon)))
+    return p
+
+
+class MpcWorkspace:
+    """Device-resident parameter block + horizon tables prepared by ``rg_mpc_setup``."""
+
+    def __init__(self, params: MpcParams, device="cuda"):
+        import torch
+        lib = load()
+        nbytes = c_size_t()
+        check(lib.rg_workspace_bytes(0, params.horizon, params.num_legs, ctypes.byref(nbytes)))
+        self.params = params
+        self.horizon = int(params.horizon)
+        self.buffer = torch.zeros(nbytes.value, dtype=torch.uint8, device=device)
+        with torch.cuda.device(self.buffer.device):
+            check(lib.rg_mpc_setup(ctypes.byref(params), c_void_p(self.buffer.data_ptr()), nbytes.value,
+                                   current_stream_ptr()))
+
+    @property
+    def ptr(self):
+        return c_void_p(self.buffer.data_ptr())
+
+
+class RobotWorkspace:
+    """Device image of the robot model (leg chains, gait, gains) prepared by ``rg_robot_setup``."""
+
+    def __init__(self, params: RobotParams, device="cuda"):
+        import torch
+        lib = load()
+        nbytes = c_size_t()
+        check(lib.rg_robot_workspace_bytes(ctypes.byref(nbytes)))
+        self.params = params
+        self.buffer = torch.zeros(nbytes.value, dtype=torch.uint8, device=device)
+        with torch.cuda.device(self.buffer.device):
+            check(lib.rg_robot_setup(ctypes.byref(params), c_void_p(self.buffer.data_ptr()), nbytes.value,
+                                     current_stream_ptr()))
+
+    @property
+    def ptr(self):
+        return c_void_p(self.buffer.data_ptr())
+
+
+def calibrate_ik(params: RobotParams, reference_motor_angles) -> None:
+    arr = (c_double * 12)(*[float(v) for v in reference_motor_angles])
+    check(load().rg_robot_calibrate_ik(ctypes.byref(params), arr))
+
+
+def mpc_build_solve(ws: MpcWorkspace, com_velocity_body, base_rpy, base_rpy_rate, foot_contact_state,
+                    foot_positions_base, command, com_height=None, contact_forces=None,
+                    horizon_forces=None, solve_info=None, want_horizon=False, want_info=True):
+    """``rg_mpc_build_solve`` on the current stream.  Returns (contact_forces, horizon_forces, solve_info)."""
+    import torch
+    n = base_rpy.shape[0]
+    dev = base_rpy.device
+    if contact_forces is None:
+        contact_forces = torch.empty((n, 12), dtype=torch.float32, device=dev)
+    if horizon_forces is None and want_horizon:
+        horizon_forces = torch.empty((n, ws.horizon, 12), dtype=torch.float32, device=dev)
+    if solve_info is None and want_info:
+        solve_info = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    hf = None if horizon_forces is None else _ptr(horizon_forces.view(n, -1), torch.float32, (ws.horizon * 12,))
+    check(load().rg_mpc_build_solve(
+        ws.ptr, n,
+        _ptr(com_velocity_body, torch.float32, (3,)), _ptr(base_rpy, torch.float32, (3,)),
+        _ptr(base_rpy_rate, torch.float32, (3,)), _ptr(foot_contact_state, torch.uint8, (4,)),
+        _ptr(foot_positions_base.view(n, -1), torch.float32, (12,)), _ptr(command, torch.float32, (3,)),
+        _ptr(com_height, torch.float32, (), allow_none=True),
+        _ptr(contact_forces, torch.float32, (12,)), hf,
+        _ptr(solve_info, torch.int32, (4,), allow_none=True), current_stream_ptr()))
+    return contact_forces, horizon_forces, solve_info
