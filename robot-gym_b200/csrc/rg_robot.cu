@@ -86,6 +86,20 @@ __host__ __device__ inline void leg_ik(const RgLegDev& L, V3 foot, double* q) {
   q[2] = wrap_pi(L.s2 * (theta - L.phi2));
   const double delta = atan2(L.l2 * sin(theta), L.l1 + L.l2 * cos(theta));
   q[1] = wrap_pi(atan2(alpha, beta) - L.psi - delta);
+  // Newton clean-up on the exact chain: the URDFs give their right angles to five digits
+  // (rpy = 1.57079), so the perpendicular/parallel-axis assumptions hold only to ~1e-5 rad.
+  for (int it = 0; it < 2; ++it) {
+    V3 jac[3];
+    const V3 err = sub(foot, leg_fk(L, q, jac));
+    const V3 c12 = cross(jac[1], jac[2]);
+    const double det = dot(jac[0], c12);
+    if (fabs(det) < 1e-12) break;                      // singular pose (straight leg): keep the closed form
+    const double d0 = dot(err, c12) / det;
+    const double d1 = dot(jac[0], cross(err, jac[2])) / det;
+    const double d2 = dot(jac[0], cross(jac[1], err)) / det;
+    if (fabs(d0) + fabs(d1) + fabs(d2) > 0.1) break;   // target out of reach: the clamped closed form stands
+    q[0] = wrap_pi(q[0] + d0); q[1] = wrap_pi(q[1] + d1); q[2] = wrap_pi(q[2] + d2);
+  }
 }
 
 // ------------------------------------------------------------------------------------ gait
@@ -376,7 +390,7 @@ __global__ void hybrid_motor_kernel(int n, const float* __restrict__ action, con
 }
 
 // ------------------------------------------------------------------------------------ host: setup
-bool near_zero(double v) { return fabs(v) < 1e-9; }
+bool near_zero(double v) { return fabs(v) < 1e-3; }   // URDF right angles are given to 5 digits
 
 int derive_ik_constants(const rg_leg_chain& c, RgLegDev& L, int leg) {
   memcpy(L.p, c.p, sizeof(L.p));
@@ -397,7 +411,7 @@ int derive_ik_constants(const rg_leg_chain& c, RgLegDev& L, int leg) {
   const V3 e2 = cross(e0, e1);
   const V3 a2_in1 = mat_mul(L.r[2], a2);          // lower axis seen from the upper-joint frame
   const double par = dot(a2_in1, a1);
-  if (fabs(fabs(par) - 1.0) > 1e-9) {
+  if (fabs(fabs(par) - 1.0) > 1e-6) {
     rg_set_error("leg %d: lower joint axis is not parallel to the upper axis (closed-form IK unsupported)", leg);
     return RG_ERR_UNSUPPORTED;
   }
@@ -426,11 +440,6 @@ int derive_ik_constants(const rg_leg_chain& c, RgLegDev& L, int leg) {
 }
 
 inline int grid_for(int n, int block) { return (n + block - 1) / block; }
-
-int fetch_robot(const void* ws) {
-  if (!ws) { rg_set_error("robot workspace is NULL"); return RG_ERR_BAD_ARG; }
-  return RG_OK;
-}
 
 }  // namespace
 

@@ -1,0 +1,282 @@
+"""Batched drop-in for ``MPCController`` (robot_gym/controllers/mpc/mpc_controller.py:14-113).
+
+Same interface -- ``update_controller_params`` / ``get_action`` / ``reset`` / ``kinematics_model`` /
+``get_standing_action`` / ``MOTOR_CONTROL_MODE`` -- but one instance drives N independent envs whose
+state lives in CUDA tensors, and every numerical step (gait generator, COM velocity estimator,
+Raibert swing controller, leg IK, convex-MPC stance QP, force -> torque, hybrid action packing)
+runs in the sm_100a kernels behind ``robot_gym.cuda`` (C ABI: include/rg_cuda.h).  The third-party
+``mpc_controller`` / ``mpc_osqp`` / PyBullet calls of the reference are not used.
+
+There is no CPU path: constructing the controller without the CUDA library or a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_void_p
+
+import numpy as np
+import torch
+
+from robot_gym import cuda as rg
+from robot_gym.controllers.controller import Controller
+from robot_gym.controllers.mpc.batched_kinematics import BatchedKinematics, robot_params_from_description
+from robot_gym.controllers.mpc.leg_state import LegState
+from robot_gym.model.robots.descriptions import MOTOR_CONTROL_HYBRID
+
+
+class _LegControllerHandle:
+    """Stands in for ``_mpc_controller.swing_leg_controller`` / ``.stance_leg_controller``: the
+    reference adapter writes ``desired_speed`` / ``desired_twisting_speed`` onto both
+    (mpc_controller.py:97-100).  Here both handles alias the controller's [N,3] command tensor."""
+
+    def __init__(self, owner):
+        self._owner = owner
+
+    @property
+    def desired_speed(self):
+        cmd = self._owner.command
+        return torch.stack([cmd[:, 0], cmd[:, 1], torch.zeros_like(cmd[:, 0])], dim=1)
+
+    @desired_speed.setter
+    def desired_speed(self, value):
+        v = torch.as_tensor(value, dtype=torch.float32, device=self._owner.device)
+        self._owner.command[:, 0] = v[..., 0]
+        self._owner.command[:, 1] = v[..., 1]
+
+    @property
+    def desired_twisting_speed(self):
+        return self._owner.command[:, 2]
+
+    @desired_twisting_speed.setter
+    def desired_twisting_speed(self, value):
+        self._owner.command[:, 2] = torch.as_tensor(value, dtype=torch.float32, device=self._owner.device)
+
+
+class _LocomotionHandle:
+    def __init__(self, owner):
+        self.swing_leg_controller = _LegControllerHandle(owner)
+        self.stance_leg_controller = _LegControllerHandle(owner)
+
+
+class BatchedMPCController(Controller):
+
+    MOTOR_CONTROL_MODE = MOTOR_CONTROL_HYBRID      # mpc_controller.py:16
+
+    def __init__(self, robot, get_time_since_reset, horizon=10, mpc_overrides=None, squeeze_single=True):
+        """``robot``: batched state provider with the getter names of robot.py (see
+        ``SyntheticRobotBatch``); ``get_time_since_reset``: callable returning a float or an
+        ``[N]`` float64 tensor (Simulation.GetTimeSinceReset, core/simulation.py:141-142)."""
+        super().__init__(robot, get_time_since_reset)
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedMPCController needs a CUDA device (no CPU fallback)")
+        rg.load()
+        self._constants = robot.GetCtrlConstants()
+        self.device = torch.device(getattr(robot, "device", "cuda"))
+        self.num_envs = int(getattr(robot, "num_envs", 1))
+        self.horizon = int(horizon)
+        self._squeeze_single = bool(squeeze_single)
+        n, dev = self.num_envs, self.device
+
+        # --- C-ABI workspaces (the analogue of _setup_controller, mpc_controller.py:28-66)
+        c = self._constants
+        self.mpc_params = rg.default_mpc_params(c.MPC_BODY_MASS, c.MPC_BODY_INERTIA, c.MPC_BODY_HEIGHT, self.horizon)
+        for key, value in (mpc_overrides or {}).items():
+            field = getattr(self.mpc_params, key)
+            if hasattr(field, "__len__"):
+                for i, v in enumerate(value):
+                    field[i] = v
+            else:
+                setattr(self.mpc_params, key, value)
+        self.robot_params = robot_params_from_description(robot, c)
+        with torch.cuda.device(dev):
+            self._mpc_ws = rg.MpcWorkspace(self.mpc_params, device=dev)
+            self._robot_ws = rg.RobotWorkspace(self.robot_params, device=dev)
+        self._kinematics = BatchedKinematics(self._robot_ws, dev)
+        self._window = int(self.robot_params.velocity_window)
+
+        # --- persistent controller state + outputs
+        f32, f64, i32, u8 = torch.float32, torch.float64, torch.int32, torch.uint8
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+        self.command = z((n, 3), f32)
+        self.vel_window = z((n, 3, self._window), f64)
+        self.vel_window_sum = z((n, 3), f64)
+        self.vel_window_corr = z((n, 3), f64)
+        self.vel_window_count = z((n,), i32)
+        self.vel_window_head = z((n,), i32)
+        self.last_leg_state = z((n, 4), i32)
+        self.phase_switch_foot_local_position = z((n, 12), f32)
+        self.swing_joint_angles = z((n, 12), f32)
+        self.swing_joint_valid = z((n, 4), u8)
+        self.desired_leg_state = z((n, 4), i32)
+        self.leg_state = z((n, 4), i32)
+        self.normalized_phase = z((n, 4), f64)
+        self.mpc_contact_state = z((n, 4), u8)
+        self.swing_foot_target = z((n, 12), f32)
+        self.com_velocity_body = z((n, 3), f32)
+        self.contact_forces = z((n, 12), f32)
+        self.motor_torques = z((n, 12), f32)
+        self.solve_info = z((n, 4), i32)
+        self.action = z((n, 60), f32)
+        self.reset_time = z((n,), f64)
+        self.time_since_reset = z((n,), f64)
+        self._mpc_controller = _LocomotionHandle(self)
+        self.update_controller_params(self.get_standing_action())
+        self.reset()
+
+    # ------------------------------------------------------------------ reference interface
+    @property
+    def kinematics_model(self):                    # mpc_controller.py:24-26 (used by robot.py:94-102)
+        return self._kinematics
+
+    @staticmethod
+    def setup_ui_params(pybullet_client):          # mpc_controller.py:68-73
+        return tuple(pybullet_client.addUserDebugParameter(name, -2., 2., 0.) for name in ("Vx", "Vy", "Wz"))
+
+    @staticmethod
+    def read_ui_params(pybullet_client, ui):       # mpc_controller.py:75-81
+        return tuple(pybullet_client.readUserDebugParameter(handle) for handle in ui)
+
+    @staticmethod
+    def get_standing_action():                     # mpc_controller.py:111-113
+        return 0., 0.
+
+    def update_controller_params(self, params):
+        """(vx, wz) / (vx, vy, wz) as scalars (broadcast to every env) or an [N,2] / [N,3] tensor;
+        the per-robot command offsets are added exactly as mpc_controller.py:83-100 does."""
+        c = self._constants
+        if isinstance(params, torch.Tensor) and params.dim() == 2:
+            p = params.to(device=self.device, dtype=torch.float32)
+            if p.shape[0] != self.num_envs or p.shape[1] not in (2, 3):
+                raise ValueError(f"expected [{self.num_envs},2] or [{self.num_envs},3], got {tuple(p.shape)}")
+            vx, wz = p[:, 0], p[:, -1]
+            vy = p[:, 1] if p.shape[1] == 3 else torch.zeros_like(vx)
+        else:
+            if len(params) == 2:
+                vx, wz = params
+                vy = 0.
+            elif len(params) == 3:
+                vx, vy, wz = params
+            else:
+                raise ValueError("params must have 2 or 3 entries")
+        self.command[:, 0] = torch.as_tensor(vx, dtype=torch.float32, device=self.device) + float(c.VX_OFFSET)
+        self.command[:, 1] = torch.as_tensor(vy, dtype=torch.float32, device=self.device) + float(c.VY_OFFSET)
+        self.command[:, 2] = torch.as_tensor(wz, dtype=torch.float32, device=self.device) + float(c.WZ_OFFSET)
+
+    def _clock(self):
+        t = self.get_time_since_reset()
+        if isinstance(t, torch.Tensor):
+            return t.to(device=self.device, dtype=torch.float64).expand(self.num_envs)
+        return torch.full((self.num_envs,), float(t), dtype=torch.float64, device=self.device)
+
+    def reset(self, env_ids=None):
+        """LocomotionController.reset (mpc_controller.py:108-109): reset_time = clock(); gait, estimator,
+        swing (latch = current feet, joint-angle store cleared) and stance state are re-armed.
+        ``env_ids`` (LongTensor) restricts the reset to a subset of envs."""
+        sel = slice(None) if env_ids is None else env_ids
+        self.reset_time[sel] = self._clock()[sel]
+        self.vel_window[sel] = 0
+        self.vel_window_sum[sel] = 0
+        self.vel_window_corr[sel] = 0
+        self.vel_window_count[sel] = 0
+        self.vel_window_head[sel] = 0
+        self.last_leg_state[sel] = -1       # "aliased" marker: the first update never latches
+        feet = self._robot.GetFootPositionsInBaseFrame().reshape(self.num_envs, 12)
+        self.phase_switch_foot_local_position[sel] = feet[sel].to(torch.float32)
+        self.swing_joint_valid[sel] = 0
+        init_state = torch.tensor([int(s) for s in self._constants.INIT_LEG_STATE], dtype=torch.int32, device=self.device)
+        self.desired_leg_state[sel] = init_state
+        self.leg_state[sel] = init_state
+        self.normalized_phase[sel] = 0
+
+    def get_action(self):
+        """``update()`` + ``get_action()`` of the third-party glue in one fused C-ABI call
+        (mpc_controller.py:102-106).  Returns the [N,60] hybrid command tensor (N == 1: a [60]
+        float32 numpy array, what Simulation.ApplyStepAction consumes)."""
+        self.step()
+        if self.num_envs == 1 and self._squeeze_single:
+            return self.action[0].cpu().numpy()
+        return self.action
+
+    # ------------------------------------------------------------------ batched step
+    def step(self):
+        r = self._robot
+        n = self.num_envs
+        torch.sub(self._clock(), self.reset_time, out=self.time_since_reset)
+        st = rg.ControllerState()
+        f32, f64, i32, u8 = torch.float32, torch.float64, torch.int32, torch.uint8
+        P = rg._ptr
+        st.time_since_reset = P(self.time_since_reset, f64)
+        st.foot_contacts = P(r.GetFootContacts(), u8, (4,))
+        st.base_velocity_world = P(r.GetBaseVelocity(), f32, (3,))
+        st.base_orientation_xyzw = P(r.GetTrueBaseOrientation(), f32, (4,))
+        st.base_rpy = P(r.GetBaseRollPitchYaw(), f32, (3,))
+        st.base_rpy_rate = P(r.GetBaseRollPitchYawRate(), f32, (3,))
+        st.foot_positions_base = P(r.GetFootPositionsInBaseFrame().view(n, 12), f32, (12,))
+        st.motor_angles = P(r.GetMotorAngles(), f32, (12,))
+        st.command = P(self.command, f32, (3,))
+        st.vel_window = P(self.vel_window, f64)
+        st.vel_window_sum = P(self.vel_window_sum, f64)
+        st.vel_window_corr = P(self.vel_window_corr, f64)
+        st.vel_window_count = P(self.vel_window_count, i32)
+        st.vel_window_head = P(self.vel_window_head, i32)
+        st.last_leg_state = P(self.last_leg_state, i32)
+        st.phase_switch_foot_local_position = P(self.phase_switch_foot_local_position, f32)
+        st.swing_joint_angles = P(self.swing_joint_angles, f32)
+        st.swing_joint_valid = P(self.swing_joint_valid, u8)
+        st.desired_leg_state = P(self.desired_leg_state, i32)
+        st.leg_state = P(self.leg_state, i32)
+        st.normalized_phase = P(self.normalized_phase, f64)
+        st.mpc_contact_state = P(self.mpc_contact_state, u8)
+        st.swing_foot_target = P(self.swing_foot_target, f32)
+        st.com_velocity_body = P(self.com_velocity_body, f32)
+        st.contact_forces = P(self.contact_forces, f32)
+        st.motor_torques = P(self.motor_torques, f32)
+        st.solve_info = P(self.solve_info, i32)
+        st.action = P(self.action, f32)
+        with torch.cuda.device(self.device):
+            rg.check(rg.load().rg_control_step(self._mpc_ws.ptr, self._robot_ws.ptr, n, ctypes.byref(st),
+                                               rg.current_stream_ptr()))
+        return self.action
+
+    # ------------------------------------------------------------------ rollout statistics
+    def rollout_stats(self):
+        """Per-rank statistics vector for the multi-GPU all-gather:
+        [solves, sum ipm iters, max ipm iters, sum polish rounds, polished count, no-stance count,
+         numeric-flag count, sum |f|_1]  (float64, on device)."""
+        info = self.solve_info
+        status = info[:, rg.RG_INFO_STATUS]
+        iters = info[:, rg.RG_INFO_IPM_ITERS].to(torch.float64)
+        return torch.stack([
+            torch.tensor(float(self.num_envs), dtype=torch.float64, device=self.device),
+            iters.sum(), iters.max(),
+            info[:, rg.RG_INFO_POLISH_ROUNDS].to(torch.float64).sum(),
+            ((status & rg.RG_STATUS_POLISHED) != 0).to(torch.float64).sum(),
+            ((status & rg.RG_STATUS_NO_STANCE) != 0).to(torch.float64).sum(),
+            ((status & rg.RG_STATUS_NUMERIC) != 0).to(torch.float64).sum(),
+            self.contact_forces.abs().to(torch.float64).sum(),
+        ])
+
+
+def shard_bounds(n_total, rank, world_size):
+    """Contiguous env range [lo, hi) of ``rank``: sizes differ by at most one."""
+    base, rem = divmod(int(n_total), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_rollout_stats(local_stats, group=None):
+    """all_gather of the small per-rank stats vector -- the ONLY collective on this path (NCCL on
+    GPUs, gloo in the CPU tests).  Returns a [world_size, len(stats)] tensor on every rank."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return local_stats.unsqueeze(0)
+    out = [torch.empty_like(local_stats) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(out, local_stats, group=group)
+    return torch.stack(out)
+
+
+def reduce_rollout_stats(gathered):
+    """Whole-job summary of gathered [R,8] stats: sums except column 2 (max)."""
+    total = gathered.sum(dim=0)
+    total[2] = gathered[:, 2].max()
+    return total

@@ -77,7 +77,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(out, file=sys.stderr)
         if proc.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs]   # cudart is linked statically (nvcc default)
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]   # static cudart (nvcc default)
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}")

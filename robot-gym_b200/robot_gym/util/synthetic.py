@@ -120,3 +120,24 @@ def make_states(n_env, description, schedule_ctrl=None, all_stance=False, nomina
         command=cmd.astype(f32),
         com_height=com_z.astype(f32),
     )
+
+
+def make_state_sequence(n_env, n_steps, description, schedule_ctrl=None, seed=SEED, control_dt_ticks=10):
+    """``n_steps`` consecutive control steps for ``n_env`` envs: every step draws a fresh random
+    state (no physics), while the clock advances like Simulation's: t = step_counter * 0.001 with
+    ACTION_REPEAT = 10 ticks per control step (core/sim_constants.py:7,11) from a per-env start."""
+    ctrl = schedule_ctrl or description.GetCtrlConstants()
+    rng = np.random.default_rng(seed + 1)
+    start = rng.integers(0, 500, int(n_env))
+    seq = []
+    for k in range(int(n_steps)):
+        st = make_states(n_env, description, schedule_ctrl=ctrl, seed=seed + 17 * (k + 1))
+        tick = start + control_dt_ticks * k
+        st.time_since_reset = (tick * 0.001).astype(np.float64)
+        planned = desired_stance(st.time_since_reset - start * 0.001, ctrl.STANCE_DURATION_SECONDS, ctrl.DUTY_FACTOR,
+                                 ctrl.INIT_PHASE_FULL_CYCLE, ctrl.INIT_LEG_STATE)
+        flip = np.random.default_rng(seed + 31 * (k + 1)).uniform(0, 1, planned.shape) < 0.08
+        st.planned_contacts = planned.astype(np.uint8)
+        st.foot_contacts = np.logical_xor(planned, flip).astype(np.uint8)
+        seq.append(st)
+    return seq

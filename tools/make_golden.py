@@ -9,7 +9,10 @@
                              (tools/extract_leg_chains.py).
 
 /root/reference does not exist on the GPU box; tests only read the committed JSON.
-Run:  python tools/make_golden.py
+  mpc_oracle_golden.npz, control_step_oracle_golden.npz : ORACLE outputs on seeded synthetic inputs
+                             (--oracle); they freeze the oracle, they are not reference outputs.
+
+Run:  python tools/make_golden.py [--oracle | --oracle-only]
 """
 import enum
 import importlib
@@ -117,5 +120,83 @@ def main():
     print("wrote", os.listdir(OUT))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--oracle-only" not in sys.argv:
     main()
+
+
+# ---------------------------------------------------------------------------------------------
+# Oracle outputs on seeded synthetic inputs (the oracle restates third-party code that cannot run
+# here, so these are "oracle goldens": they freeze the oracle's answers so that the GPU tests on
+# the GPU box and future oracle edits are both checked against the same committed numbers).
+def make_oracle_goldens():
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "robot-gym_b200"))
+    from oracle import convex_mpc, kinematics, locomotion
+    from robot_gym.model.robots.descriptions import GHOST
+    from robot_gym.util import synthetic
+
+    ctrl = GHOST.GetCtrlConstants()
+    out = {}
+    for horizon, n in ((10, 96), (5, 24), (20, 12)):
+        st = synthetic.make_states(n, GHOST, seed=synthetic.SEED + horizon)
+        mp = convex_mpc.MpcParams(horizon=horizon)
+        forces = np.zeros((n, horizon * 12))
+        for i in range(n):
+            forces[i] = convex_mpc.compute_contact_forces(
+                mp, st.com_velocity_body[i].astype(np.float64), st.base_rpy[i].astype(np.float64),
+                st.base_rpy_rate[i].astype(np.float64), st.planned_contacts[i],
+                st.foot_positions_base[i].astype(np.float64), [0, 0, ctrl.MPC_BODY_HEIGHT],
+                [float(st.command[i, 0]), float(st.command[i, 1]), 0.0], [0, 0, 0], [0, 0, float(st.command[i, 2])])
+        out[f"mpc_h{horizon}_forces"] = forces
+        out[f"mpc_h{horizon}_n"] = np.array(n)
+    np.savez_compressed(os.path.join(OUT, "mpc_oracle_golden.npz"), **out)
+
+    # full control step: 6 envs x 40 steps through the restated LocomotionController
+    n_env, n_steps = 6, 40
+    seq = synthetic.make_state_sequence(n_env, n_steps, GHOST)
+    actions = np.zeros((n_steps, n_env, 60), dtype=np.float32)
+    desired = np.zeros((n_steps, n_env, 4), dtype=np.int32)
+    state = np.zeros((n_steps, n_env, 4), dtype=np.int32)
+    phase = np.zeros((n_steps, n_env, 4), dtype=np.float64)
+    forces = np.zeros((n_steps, n_env, 12), dtype=np.float64)
+    vbody = np.zeros((n_steps, n_env, 3), dtype=np.float64)
+    for e in range(n_env):
+        robot = kinematics.OracleRobot(GHOST)
+        clock = {"t": 0.0}
+        def load(k):
+            s = seq[k]
+            robot.set_state(base_velocity=s.base_velocity_world[e].astype(np.float64),
+                            base_orientation=s.base_orientation_xyzw[e].astype(np.float64),
+                            base_rpy=s.base_rpy[e].astype(np.float64), base_rpy_rate=s.base_rpy_rate[e].astype(np.float64),
+                            foot_positions=s.foot_positions_base[e].astype(np.float64), foot_contacts=s.foot_contacts[e],
+                            motor_angles=s.motor_angles[e].astype(np.float64))
+            clock["t"] = float(s.time_since_reset[e])
+        load(0)
+        ctl = locomotion.build_mpc_controller(robot, lambda: clock["t"], ctrl)
+        ctl.reset()
+        for k in range(n_steps):
+            load(k)
+            s = seq[k]
+            locomotion.update_controller_params(ctl, ctrl, (float(s.command[e, 0] - np.float32(ctrl.VX_OFFSET)),
+                                                            float(s.command[e, 1] - np.float32(ctrl.VY_OFFSET)),
+                                                            float(s.command[e, 2] - np.float32(ctrl.WZ_OFFSET))))
+            # use the float32 command the GPU path sees
+            ctl.swing_leg_controller.desired_speed = [float(s.command[e, 0]), float(s.command[e, 1]), 0.0]
+            ctl.swing_leg_controller.desired_twisting_speed = float(s.command[e, 2])
+            ctl.stance_leg_controller.desired_speed = [float(s.command[e, 0]), float(s.command[e, 1]), 0.0]
+            ctl.stance_leg_controller.desired_twisting_speed = float(s.command[e, 2])
+            ctl.update()
+            actions[k, e] = ctl.get_action()
+            desired[k, e] = ctl.gait_generator.desired_leg_state
+            state[k, e] = ctl.gait_generator.leg_state
+            phase[k, e] = ctl.gait_generator.normalized_phase
+            forces[k, e] = ctl.stance_leg_controller.last_contact_forces
+            vbody[k, e] = ctl.state_estimator.com_velocity_body_frame
+    np.savez_compressed(os.path.join(OUT, "control_step_oracle_golden.npz"), actions=actions, desired_leg_state=desired,
+                        leg_state=state, normalized_phase=phase, contact_forces=forces, com_velocity_body=vbody,
+                        n_env=np.array(n_env), n_steps=np.array(n_steps))
+    print("oracle goldens written")
+
+
+if __name__ == "__main__" and ("--oracle" in sys.argv or "--oracle-only" in sys.argv):
+    make_oracle_goldens()
