@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Benchmark of the batched MPC stance solve (BASELINE.json metric: MPC stance solves/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on host cores
+
+A "step" is one pass of rg_mpc_build_solve over one batch of synthetic robot states: BASELINE
+config[1] -- 4096 envs per GPU, horizon 10, 4 legs, friction pyramid (weak scaling: every rank
+solves its own contiguous 4096-env shard of one seeded global batch; the only collective is one
+all-gather of the 8-float rollout statistics per timed window).  Prints ONE JSON line (rank 0).
+
+  value        whole-job solves/s with the inputs resident in HBM (CUDA events around each step)
+  e2e          the same metric through the public API from HOST buffers: pinned host -> device copy
+               of the step's inputs, solve, device -> host read of the forces, all inside the timing
+  roofline     HBM roofline of the solve kernel (algorithmic 156 B/solve; this path is NOT HBM-bound,
+               the fraction is reported as it is) + roofline_fp64: executed-FLOP fraction of the
+               measured FP64 FMA peak, the resource that actually binds
+  cpu_baseline the oracle port (oracle/c/mpc_oracle.c, dense formulation + dense interior point) on
+               the host cores; reference parity is unpinned and motion_imitation/OSQP cannot run
+               offline, so kind = "port"
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(REPO, "robot-gym_b200"))
+sys.path.insert(0, REPO)
+
+ENVS_PER_GPU = 4096
+HORIZON = 10
+METRIC = "mpc_stance_solves_per_sec"
+UNIT = "solves/s"
+ALGO_BYTES_PER_SOLVE = 156            # 108 B in + 48 B out
+# algorithmic FLOPs per solve in the dense-reference formulation:
+# Hessian 3744 h^3 + gradient + Cholesky 576 h^3 + 0.033 MFLOP per solver iteration at h = 10
+ALGO_FLOPS_FIXED = 4.36e6
+ALGO_FLOPS_PER_ITER = 0.033e6
+
+
+def _measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def _dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def _config(n_gpus, extra=None):
+    cfg = {"workload": f"BASELINE config[1]: {ENVS_PER_GPU} synthetic quadruped states per GPU, batched MPC stance QP "
+                       f"(horizon {HORIZON}, 4 legs, friction pyramid), ghost parameters, trot contact schedule",
+           "envs_per_gpu": ENVS_PER_GPU, "global_envs": ENVS_PER_GPU * n_gpus, "horizon": HORIZON,
+           "sharding": "contiguous env shards of one seeded global batch; all-gather of 8 rollout stats per window",
+           "l2": "flushed between timed steps (256 MiB device memset, outside the timed interval)"}
+    cfg.update(extra or {})
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def run_reference(args):
+    """`--impl reference`: the CPU implementation of the path (oracle port; the reference's own
+    motion_imitation/OSQP/PyBullet stack cannot be installed offline) on all host threads."""
+    rank, world, _ = _dist_env()
+    if rank != 0:
+        return
+    from oracle import c_oracle, convex_mpc
+    from robot_gym.model.robots.descriptions import GHOST
+    from robot_gym.util import synthetic
+    ctrl = GHOST.GetCtrlConstants()
+    cores = os.cpu_count() or 1
+    n = ENVS_PER_GPU
+    states = synthetic.make_states(ENVS_PER_GPU * args.gpus, GHOST).slice(0, n)
+    mp = convex_mpc.MpcParams(horizon=HORIZON, mass=ctrl.MPC_BODY_MASS, inertia=tuple(ctrl.MPC_BODY_INERTIA))
+    for _ in range(max(1, min(args.warmup, 2))):
+        c_oracle.solve_batch(mp, states.slice(0, 512), ctrl.MPC_BODY_HEIGHT, n_threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c_oracle.solve_batch(mp, states, ctrl.MPC_BODY_HEIGHT, n_threads=cores)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": _config(args.gpus, {"note": "CPU arm processes one 4096-env shard per step on rank 0"}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{n} envs per step x {args.steps} steps, oracle/c/mpc_oracle.c (dense condensed "
+                                       "build + dense Mehrotra interior point), one pthread per host core; "
+                                       "NOT motion_imitation/OSQP (unavailable offline, parity unpinned)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from robot_gym import cuda as rg
+    from robot_gym.controllers.mpc.batched_mpc_controller import (BatchedMPCController, gather_rollout_stats,
+                                                                  reduce_rollout_stats, shard_bounds)
+    from robot_gym.model.robots.descriptions import GHOST
+    from robot_gym.model.robots.synthetic_robot import SyntheticRobotBatch
+    from robot_gym.util import synthetic
+
+    rank, world, local = _dist_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback for the solve kernels")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world:
+        raise RuntimeError(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run")
+    rg.load()                                  # fails loudly if librg_cuda.so is missing
+
+    ctrl = GHOST.GetCtrlConstants()
+    n_global = ENVS_PER_GPU * world
+    lo, hi = shard_bounds(n_global, rank, world)
+    states = synthetic.make_states(n_global, GHOST).slice(lo, hi)      # sharding-invariant inputs
+    n = hi - lo
+    params = rg.default_mpc_params(ctrl.MPC_BODY_MASS, ctrl.MPC_BODY_INERTIA, ctrl.MPC_BODY_HEIGHT, HORIZON)
+    ws = rg.MpcWorkspace(params, device=dev)
+
+    host_names = ("com_velocity_body", "base_rpy", "base_rpy_rate", "planned_contacts", "foot_positions_base", "command")
+    host = {k: torch.from_numpy(np.ascontiguousarray(getattr(states, k))).pin_memory() for k in host_names}
+    dev_in = {k: v.to(dev) for k, v in host.items()}
+    forces = torch.empty((n, 12), dtype=torch.float32, device=dev)
+    info = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    forces_host = torch.empty((n, 12), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def solve(inputs):
+        rg.mpc_build_solve(ws, inputs["com_velocity_body"], inputs["base_rpy"], inputs["base_rpy_rate"],
+                           inputs["planned_contacts"], inputs["foot_positions_base"], inputs["command"],
+                           contact_forces=forces, solve_info=info)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(max(3, args.warmup)):
+        solve(dev_in)
+    barrier()
+
+    # ---- timed: K steps, device-resident inputs, CUDA events on the launching (current) stream
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = rg.launch_count()
+    barrier()
+    t_wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.zero_()                       # L2 flush, outside the timed interval
+        a.record()
+        solve(dev_in)
+        b.record()
+    stats = None
+    if world > 1:
+        # the path's only collective: one all-gather of the small rollout-statistics vector
+        s_local = _stats_vector(torch, rg, info, forces, n)
+        stats = gather_rollout_stats(s_local)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = rg.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = n_global * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers in, host forces out, copies inside the timed region
+    def e2e_step():
+        inputs = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        solve(inputs)
+        forces_host.copy_(forces, non_blocking=True)
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    e2e_ms = torch.tensor([max(e0.elapsed_time(e1), e2e_wall * 1e3)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = n_global * args.steps / (float(e2e_ms.item()) * 1e-3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values()) * world
+    d2h = forces_host.numel() * forces_host.element_size() * world
+
+    # ---- solver statistics (whole job)
+    s_local = _stats_vector(torch, rg, info, forces, n)
+    gathered = gather_rollout_stats(s_local) if world > 1 else s_local.unsqueeze(0)
+    total = reduce_rollout_stats(gathered).cpu().numpy()
+    iters_mean = float(total[1] / total[0])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- rank 0 only: roofline numbers, FMA peaks, CPU baseline, control-step extras
+    peaks, peak_kind = _measured_peaks()
+    kernel_ms = statistics.mean(step_ms)          # one kernel launch per step: the step time IS the kernel time
+    algo_bytes = ALGO_BYTES_PER_SOLVE * n
+    achieved_gbs = algo_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(REPO, "profiles", "r01_mpc_ncu_summary.json")
+    if os.path.exists(prof):
+        with open(prof) as fh:
+            traffic = json.load(fh).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": f"of {peak_kind}",
+                "kernel": "mpc_solve_kernel<10>", "kernel_ms": kernel_ms,
+                "note": "the solve keeps the whole QP on chip: HBM is not the binding resource (see roofline_fp64)"}
+    fp64_peak = rg.measure_fma_peak(True)
+    fp32_peak = rg.measure_fma_peak(False)
+    polish_mean = float(total[3] / total[0])
+    algo_flops = (ALGO_FLOPS_FIXED + ALGO_FLOPS_PER_ITER * (iters_mean + polish_mean)) * n
+    roofline_fp64 = {"bound": "fp64 fma", "algorithmic_tflops": algo_flops / (kernel_ms * 1e-3) / 1e12,
+                     "peak_fp64_tflops_measured": fp64_peak, "peak_fp32_tflops_measured": fp32_peak,
+                     "algorithmic_frac_of_fp64_peak": algo_flops / (kernel_ms * 1e-3) / 1e12 / fp64_peak,
+                     "note": "algorithmic FLOPs are the dense-reference count (SURVEY.md 8d); the kernel's closed-form / "
+                             "Woodbury formulation executes ~10x fewer (see profiles/ for the ncu executed-FLOP count)"}
+
+    cpu = _cpu_baseline(states, ctrl)
+    control = _control_step_extras(torch, rg, BatchedMPCController, SyntheticRobotBatch, synthetic, GHOST, dev)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": _config(world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_fp64": roofline_fp64,
+            "cpu_baseline": cpu,
+            "solver": {"ipm_iters_mean": iters_mean, "ipm_iters_max": float(total[2]), "polish_rounds_mean": polish_mean,
+                       "polished_fraction": float(total[4] / total[0]), "numeric_flags": float(total[6])},
+            "latency": {"solve_p50_ms": statistics.median(step_ms), "solve_max_ms": max(step_ms), "envs": n},
+            "control_step": control, "wall_s_timed_region": t_wall}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _stats_vector(torch, rg, info, forces, n):
+    status = info[:, rg.RG_INFO_STATUS]
+    iters = info[:, rg.RG_INFO_IPM_ITERS].to(torch.float64)
+    return torch.stack([
+        torch.tensor(float(n), dtype=torch.float64, device=info.device), iters.sum(), iters.max(),
+        info[:, rg.RG_INFO_POLISH_ROUNDS].to(torch.float64).sum(),
+        ((status & rg.RG_STATUS_POLISHED) != 0).to(torch.float64).sum(),
+        ((status & rg.RG_STATUS_NO_STANCE) != 0).to(torch.float64).sum(),
+        ((status & rg.RG_STATUS_NUMERIC) != 0).to(torch.float64).sum(),
+        forces.abs().to(torch.float64).sum()])
+
+
+def _cpu_baseline(states, ctrl):
+    """The oracle port timed on this box's host cores on the same 4096-env batch (bounded sample)."""
+    try:
+        from oracle import c_oracle, convex_mpc
+        cores = os.cpu_count() or 1
+        mp = convex_mpc.MpcParams(horizon=HORIZON, mass=ctrl.MPC_BODY_MASS, inertia=tuple(ctrl.MPC_BODY_INERTIA))
+        c_oracle.solve_batch(mp, states.slice(0, 256), ctrl.MPC_BODY_HEIGHT, n_threads=cores)
+        best = 0.0
+        reps = 2
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            c_oracle.solve_batch(mp, states, ctrl.MPC_BODY_HEIGHT, n_threads=cores)
+            best = max(best, len(states) / (time.perf_counter() - t0))
+        return {"value": best, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"the same {len(states)}-env batch, best of {reps} passes, oracle/c/mpc_oracle.c on {cores} "
+                          "pthreads (restated CPU oracle, NOT motion_imitation/OSQP which is unavailable offline)"}
+    except Exception as exc:   # the baseline is a reported number, never a reason to lose the GPU measurement
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
+
+
+def _control_step_extras(torch, rg, Controller, RobotBatch, synthetic, desc, dev):
+    """BASELINE config 3 in short: full control step (gait + estimator + swing + IK + MPC + pack) on
+    65536 envs; p50 latency over a few repetitions."""
+    try:
+        n = 65536
+        robot = RobotBatch(desc, synthetic.make_states(n, desc), device=dev)
+        ctl = Controller(robot, robot.GetTimeSinceReset)
+        ctl.command.copy_(torch.from_numpy(synthetic.make_states(n, desc).command).to(dev))
+        for _ in range(2):
+            ctl.step()
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ctl.step()
+            b.record()
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+        p50 = statistics.median(times)
+        return {"envs": n, "p50_ms": p50, "env_steps_per_s": n / (p50 * 1e-3), "launches_per_step": 3,
+                "workload": "BASELINE config[2]: full control step, 65536 envs, 1 GPU"}
+    except Exception as exc:
+        return {"error": str(exc)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

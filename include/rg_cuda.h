@@ -82,8 +82,8 @@ typedef struct rg_mpc_params {
   double desired_body_height;  /* desired_com_position[2] */
   /* solver controls (not in the reference: OSQP eps/polish have no equivalent here) */
   double ipm_tol;              /* relative residual at which the interior point hands over (1e-6) */
-  int32_t max_ipm_iters;       /* hard cap (30) */
-  int32_t max_polish_rounds;   /* 0 disables the active-set polish (4) */
+  int32_t max_ipm_iters;       /* hard cap (40) */
+  int32_t max_polish_rounds;   /* 0 disables the active-set polish; rounds per attempt (3) */
 } rg_mpc_params;
 
 /* Fill `p` with the motion_imitation defaults for the given mass/inertia/height. */
@@ -256,6 +256,10 @@ int rg_control_step(const void* mpc_workspace, const void* robot_workspace, int 
  * tau = -kp (q - q_des) - kd (qd - qd_des) + tau_ff ; no clipping (robot.py:40-45). */
 int rg_hybrid_motor_torque(int n_env, const float* action, const float* motor_angles,
                            const float* motor_velocities, float* motor_torques, void* stream);
+
+/* Diagnostic (synchronises the device): best-of-4 CUDA-core FMA throughput in TFLOP/s, fp32 or fp64,
+ * the roofline denominator for the solve kernel (MEASURED_PEAKS.json has no CUDA-core peak). */
+int rg_measure_fma_peak(int use_fp64, int iters, double* tflops_host);
 
 /* Counters for bench.py's gpu_launches claim: number of kernels this library launched since load. */
 uint64_t rg_launch_count(void);

@@ -179,7 +179,7 @@ extern "C" int rg_mpc_default_params(rg_mpc_params* p, double mass, const double
   p->fz_min = mass * 9.8 * 0.1;
   p->desired_body_height = desired_body_height;
   p->ipm_tol = 1e-6;
-  p->max_ipm_iters = 30;
+  p->max_ipm_iters = 40;
   p->max_polish_rounds = 3;
   return RG_OK;
 }
@@ -226,7 +226,7 @@ extern "C" int rg_mpc_setup(const rg_mpc_params* p, void* workspace, size_t work
   memset(&h, 0, sizeof(h));
   h.magic = RG_WS_MAGIC_MPC;
   h.horizon = p->horizon;
-  h.max_ipm_iters = p->max_ipm_iters > 0 ? p->max_ipm_iters : 30;
+  h.max_ipm_iters = p->max_ipm_iters > 0 ? p->max_ipm_iters : 40;
   h.max_polish_rounds = p->max_polish_rounds;
   h.inv_mass = 1.0 / p->mass;
   if (!inv3(p->inertia, h.inv_inertia)) { rg_set_error("inertia matrix is singular"); return RG_ERR_SINGULAR; }
@@ -273,4 +273,54 @@ extern "C" int rg_mpc_build_solve(const void* workspace, int n_env, const float*
   return rg_launch_mpc((const RgMpcDev*)workspace, horizon, n_env, com_velocity_body, base_rpy, base_rpy_rate,
                        foot_contact_state, foot_positions_base, command, com_height, 0, contact_forces, horizon_forces,
                        solve_info, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Diagnostic: measured CUDA-core FMA peak (the roofline denominator this path is actually bound by;
+// MEASURED_PEAKS.json only has HBM and bf16 tensor numbers).  8 independent FMA chains per thread.
+namespace {
+template <typename T>
+__global__ void fma_peak_kernel(T* out, int iters, T a, T b) {
+  T x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+    x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+template <typename T>
+int measure_fma(int iters, double* tflops) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = sms * 8, threads = 256;
+  T* buf = nullptr;
+  int rc = rg_check_cuda(cudaMalloc(&buf, sizeof(T) * blocks * threads), "fma peak cudaMalloc");
+  if (rc != RG_OK) return rc;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    fma_peak_kernel<T><<<blocks, threads>>>(buf, iters, (T)0.999, (T)0.001);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    if (rep > 0 && ms > 0.f) best = fmax(best, flops / (ms * 1e-3) * 1e-12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  *tflops = best;
+  return rg_check_cuda(cudaGetLastError(), "fma peak kernel");
+}
+}  // namespace
+
+extern "C" int rg_measure_fma_peak(int use_fp64, int iters, double* tflops_host) {
+  if (!tflops_host || iters <= 0) { rg_set_error("rg_measure_fma_peak: bad argument"); return RG_ERR_BAD_ARG; }
+  return use_fp64 ? measure_fma<double>(iters, tflops_host) : measure_fma<float>(iters, tflops_host);
 }

@@ -649,9 +649,9 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
         for (int d = 0; d < 3; ++d) u_best[d] = u[d];
       }
       if (res < tol) { converged = true; break; }
-      stall = (res > 0.9 * prev_res) ? stall + 1 : 0;
+      stall = (res > 0.9 * prev_res && res < 1e-7) ? stall + 1 : 0;   // only near the numerical floor
       prev_res = res;
-      if (iters >= max_iters || stall >= 3 || !(res == res)) { ipm_dead = true; break; }
+      if (iters >= max_iters || stall >= 4 || !(res == res)) { ipm_dead = true; break; }
       ++iters;
 
       // block 3x3 parts and Psi

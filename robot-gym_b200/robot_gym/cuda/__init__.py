@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     "rg_robot_calibrate_ik", "rg_robot_workspace_bytes", "rg_robot_setup",
     "rg_gait_step", "rg_com_velocity_update", "rg_swing_targets", "rg_leg_ik", "rg_leg_fk",
     "rg_force_to_torque", "rg_pack_hybrid_action", "rg_control_step", "rg_hybrid_motor_torque",
-    "rg_launch_count", "rg_last_error", "rg_version",
+    "rg_measure_fma_peak", "rg_launch_count", "rg_last_error", "rg_version",
 )
 
 
@@ -122,6 +122,7 @@ def load(build_if_missing: bool = False):
     lib.rg_pack_hybrid_action.argtypes = [c_void_p, c_int] + [c_void_p] * 5 + [c_void_p]
     lib.rg_control_step.argtypes = [c_void_p, c_void_p, c_int, POINTER(ControllerState), c_void_p]
     lib.rg_hybrid_motor_torque.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.rg_measure_fma_peak.argtypes = [c_int, c_int, POINTER(c_double)]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("rg_last_error", "rg_version", "rg_launch_count"):
@@ -133,6 +134,13 @@ def load(build_if_missing: bool = False):
 def check(code: int):
     if code != 0:
         raise RgCudaError(code, load().rg_last_error().decode())
+
+
+def measure_fma_peak(fp64: bool, iters: int = 1 << 15) -> float:
+    """Measured CUDA-core FMA peak in TFLOP/s (diagnostic; synchronises the device)."""
+    out = c_double()
+    check(load().rg_measure_fma_peak(1 if fp64 else 0, int(iters), ctypes.byref(out)))
+    return float(out.value)
 
 
 def launch_count() -> int:

@@ -36,7 +36,8 @@ def test_gait_step_is_bit_exact(rg_lib, cuda_device, schedule):
     state = torch.empty_like(desired)
     phase = torch.empty((n, 4), dtype=torch.float64, device=cuda_device)
     p = ctypes.c_void_p
-    rg.check(rg_lib.rg_gait_step(ws.ptr, n, p(_dev(t, cuda_device).data_ptr()), p(_dev(contacts, cuda_device).data_ptr()),
+    t_dev, c_dev = _dev(t, cuda_device), _dev(contacts, cuda_device)     # keep alive across the launch
+    rg.check(rg_lib.rg_gait_step(ws.ptr, n, p(t_dev.data_ptr()), p(c_dev.data_ptr()),
                                  p(desired.data_ptr()), p(state.data_ptr()), p(phase.data_ptr()), None))
     torch.cuda.synchronize()
     robot = kinematics.OracleRobot(desc)
