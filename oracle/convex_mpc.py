@@ -350,7 +350,10 @@ def solve_qp(p_mat, q_vec, c_mat, lb, ub, tol=1e-10, max_iter=60, polish=True):
             break
         d = lam / s
         phi = pm + gm.T @ (d[:, None] * gm)
-        cho = scipy.linalg.cho_factor(phi)
+        try:
+            cho = scipy.linalg.cho_factor(phi)
+        except np.linalg.LinAlgError:
+            break       # deep iterate lost positive definiteness to rounding: the polish takes over from here
 
         def newton(r_c):
             rhs = -r_d - gm.T @ ((-r_c + lam * r_p) / s)

@@ -26,6 +26,20 @@
 #include "rg_common.cuh"
 #include <math.h>
 
+#ifdef RG_DEBUG_TRACE
+// debug builds only (RG_DEBUG_TRACE=1 python -m robot_gym.cuda.build): per-iteration trace of one env
+__device__ double* g_trace = nullptr;
+__device__ int g_trace_env = -1;
+extern "C" int rg_debug_set_trace(double* dev_buf, int env) {
+  cudaMemcpyToSymbol(g_trace, &dev_buf, sizeof(dev_buf));
+  cudaMemcpyToSymbol(g_trace_env, &env, sizeof(env));
+  return 0;
+}
+#define RG_TRACE(slot, value) do { if (g_trace && env == g_trace_env && threadIdx.x == 0) g_trace[slot] = (value); } while (0)
+#else
+#define RG_TRACE(slot, value) do { } while (0)
+#endif
+
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
@@ -624,11 +638,13 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   // Escalation ladder: interior point to `tol`, then the active-set polish; if the polish does not
   // verify within its round budget (weakly active constraints: multipliers of order alpha), drive
   // the interior point 100x further and try again.  Last resort: the best interior-point iterate.
+  int trace_n = 0;
+  (void)trace_n;
   double best_res = 1e300, prev_res = 1e300;
   double u_best[3] = {u[0], u[1], u[2]};
   int stall = 0;
   bool done = false;
-  for (int attempt = 0; attempt < 4 && !done; ++attempt) {
+  for (int attempt = 0; attempt < 3 && !done; ++attempt) {
     bool converged = false, ipm_dead = false;
     while (true) {
       double pu[3], rd[3], gl[3];
@@ -643,6 +659,8 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       block_reduce<C::NW>(sl, rdmax, dmn, sm.red);
       const double mu_c = sl / m_total;
       const double res = fmax(rdmax, mu_c) / qscale;
+      RG_TRACE(4 * trace_n + 0, res); RG_TRACE(4 * trace_n + 1, mu_c); RG_TRACE(4 * trace_n + 2, (double)iters); RG_TRACE(4 * trace_n + 3, tol);
+      ++trace_n;
       if (res < best_res) {
         best_res = res;
 #pragma unroll
@@ -651,7 +669,12 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       if (res < tol) { converged = true; break; }
       stall = (res > 0.9 * prev_res && res < 1e-7) ? stall + 1 : 0;   // only near the numerical floor
       prev_res = res;
-      if (iters >= max_iters || stall >= 4 || !(res == res)) { ipm_dead = true; break; }
+      // dead: budget spent, stalled at the numerical floor, NaN, or diverging (deep iterates lose the
+      // tiny slacks of active rows to cancellation in ds = -G dx)
+      if (iters >= max_iters || stall >= 4 || !(res == res) || (res > 1e3 * best_res && best_res < 1e-6)) {
+        ipm_dead = true;
+        break;
+      }
       ++iters;
 
       // block 3x3 parts and Psi
@@ -737,8 +760,8 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     }
     if (converged) status |= RG_STATUS_IPM_CONVERGED; else status &= ~RG_STATUS_IPM_CONVERGED;
     if (max_polish <= 0) {
-      if (ipm_dead || tol <= 1e-12) break;
-      tol = 1e-12;       // without the polish the interior point itself has to resolve the alpha-directions
+      if (ipm_dead || tol <= 1e-9) break;
+      tol = 1e-9;        // without the polish the interior point itself has to resolve the alpha-directions
       continue;
     }
 
@@ -748,7 +771,8 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     for (int r = 0; r < 10; ++r) if (active_blk && lam[r] > s[r]) act |= 1u << r;
     bool polished = false;
     double up[3] = {0.0, 0.0, 0.0};
-    for (int round = 0; round < max_polish; ++round) {
+    const int round_budget = max_polish << attempt;   // 3, 6, 12: later attempts start from a sharper guess
+    for (int round = 0; round < round_budget; ++round) {
       ++polish_rounds;
       // --- per block: orthonormal basis of the active normals (<= 3), null-space basis Z, u0
       double e[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
@@ -906,6 +930,12 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       double changed = (act_new != act) ? 1.0 : 0.0, dmx = 0.0, dmn = 0.0;
       block_reduce<C::NW>(changed, dmx, dmn, sm.red);
       act = act_new;
+      {
+        double cnt = (double)__popc(act), dmx2 = 0.0, dmn2 = 0.0;
+        block_reduce<C::NW>(cnt, dmx2, dmn2, sm.red);
+        RG_TRACE(4 * trace_n + 0, -1.0); RG_TRACE(4 * trace_n + 1, changed); RG_TRACE(4 * trace_n + 2, cnt); RG_TRACE(4 * trace_n + 3, (double)round);
+        ++trace_n;
+      }
       if (changed == 0.0) { polished = true; break; }
     }
     if (polished) {
@@ -919,7 +949,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       break;
     }
     if (ipm_dead) break;
-    tol = fmax(tol * 1e-2, 1e-13);
+    tol = fmax(tol * 1e-2, 1e-9);   // float64 interior-point iterates are trustworthy down to ~1e-9 here
   }
   if (!done) {
 #pragma unroll

@@ -146,8 +146,10 @@ def test_contact_schedules_config4(rg_lib, cuda_device, schedule):
     desc = with_gait(GHOST, schedule)
     st = synthetic.make_states(512, desc, schedule_ctrl=desc.GetCtrlConstants(), seed=31)
     f, hf, info, _ = _run(rg_lib, cuda_device, st)
-    assert np.all(info[:, rg.RG_INFO_STATUS] & rg.RG_STATUS_POLISHED)
-    for i in range(0, 512, 64):
+    polished = (info[:, rg.RG_INFO_STATUS] & rg.RG_STATUS_POLISHED) != 0
+    assert polished.mean() >= 0.995, (schedule, polished.mean())
+    # every env the polish did not verify (degenerate vertices under pace/bound) is checked individually
+    for i in list(range(0, 512, 64)) + list(np.flatnonzero(~polished)):
         assert _rel(hf[i].reshape(-1), _oracle(st, i)) < REL_TOL, (schedule, i)
 
 
