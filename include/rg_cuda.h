@@ -97,6 +97,9 @@ int rg_workspace_bytes(int n_env, int horizon, int num_legs, size_t* bytes_host)
  * the parameters into `workspace`.  Synchronises `stream`. */
 int rg_mpc_setup(const rg_mpc_params* p_host, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Forget a workspace prepared by rg_mpc_setup (call before freeing or reusing its memory). */
+int rg_mpc_release(const void* workspace);
+
 /* Replaces: ConvexMpc.compute_contact_forces(com_position=[0], com_velocity, rpy,
  * angular_velocity, foot_contact_states, foot_positions_base_frame, friction, desired...)
  * as called by TorqueStanceLegController.get_action (mpc_controller.py:47-56,105).

@@ -255,18 +255,24 @@ extern "C" int rg_mpc_setup(const rg_mpc_params* p, void* workspace, size_t work
   return RG_OK;
 }
 
+extern "C" int rg_mpc_release(const void* workspace) {
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  g_ws_horizon.erase(workspace);
+  return RG_OK;
+}
+
 extern "C" int rg_mpc_build_solve(const void* workspace, int n_env, const float* com_velocity_body,
                                   const float* base_rpy, const float* base_rpy_rate,
                                   const uint8_t* foot_contact_state, const float* foot_positions_base,
                                   const float* command, const float* com_height, float* contact_forces,
                                   float* horizon_forces, int32_t* solve_info, void* stream) {
+  if (n_env == 0) return RG_OK;   // empty batch: nothing to validate, nothing to launch
   if (!workspace || !com_velocity_body || !base_rpy || !base_rpy_rate || !foot_contact_state ||
       !foot_positions_base || !command || !contact_forces) {
     rg_set_error("rg_mpc_build_solve: NULL argument");
     return RG_ERR_BAD_ARG;
   }
   if (n_env < 0) { rg_set_error("rg_mpc_build_solve: n_env < 0"); return RG_ERR_BAD_ARG; }
-  if (n_env == 0) return RG_OK;
   int horizon = 0;
   int rc = rg_mpc_workspace_horizon(workspace, &horizon);
   if (rc != RG_OK) return rc;

@@ -542,8 +542,8 @@ extern "C" int rg_robot_setup(const rg_robot_params* p, void* ws, size_t bytes, 
 
 extern "C" int rg_gait_step(const void* ws, int n_env, const double* t, const uint8_t* contacts,
                             int32_t* desired, int32_t* state, double* nphase, void* stream) {
+  if (n_env == 0) return RG_OK;   // empty batch: nothing to validate, nothing to launch
   RG_REQUIRE(ws && t && contacts && desired && state && nphase && n_env >= 0, "rg_gait_step");
-  if (n_env == 0) return RG_OK;
   gait_kernel<<<grid_for(4 * n_env, 256), 256, 0, (cudaStream_t)stream>>>((const RgRobotDev*)ws, n_env, t, contacts, desired, state, nphase);
   rg_count_launch();
   return rg_check_cuda(cudaGetLastError(), "gait_kernel launch");
@@ -552,8 +552,8 @@ extern "C" int rg_gait_step(const void* ws, int n_env, const double* t, const ui
 extern "C" int rg_com_velocity_update(const void* ws, int n_env, const float* vel_world, const float* quat,
                                       double* window, double* wsum, double* wcorr, int32_t* wcount, int32_t* whead,
                                       float* v_body, float* v_world, void* stream) {
+  if (n_env == 0) return RG_OK;   // empty batch: nothing to validate, nothing to launch
   RG_REQUIRE(ws && vel_world && quat && window && wsum && wcorr && wcount && whead && v_body && n_env >= 0, "rg_com_velocity_update");
-  if (n_env == 0) return RG_OK;
   com_velocity_kernel<<<grid_for(n_env, 128), 128, 0, (cudaStream_t)stream>>>((const RgRobotDev*)ws, n_env, vel_world, quat, window,
                                                                              wsum, wcorr, wcount, whead, v_body, v_world);
   rg_count_launch();
@@ -563,9 +563,9 @@ extern "C" int rg_com_velocity_update(const void* ws, int n_env, const float* ve
 extern "C" int rg_swing_targets(const void* ws, int n_env, const int32_t* desired, const int32_t* state,
                                 const double* nphase, const float* feet, const float* v_body, const float* rpy_rate,
                                 const float* cmd, int32_t* last_state, float* latch, float* target, void* stream) {
+  if (n_env == 0) return RG_OK;   // empty batch: nothing to validate, nothing to launch
   RG_REQUIRE(ws && desired && state && nphase && feet && v_body && rpy_rate && cmd && last_state && latch && target && n_env >= 0,
              "rg_swing_targets");
-  if (n_env == 0) return RG_OK;
   swing_kernel<<<grid_for(4 * n_env, 256), 256, 0, (cudaStream_t)stream>>>((const RgRobotDev*)ws, n_env, desired, state, nphase, feet,
                                                                           v_body, rpy_rate, cmd, last_state, latch, target);
   rg_count_launch();
@@ -573,24 +573,24 @@ extern "C" int rg_swing_targets(const void* ws, int n_env, const int32_t* desire
 }
 
 extern "C" int rg_leg_ik(const void* ws, int n_env, const float* foot, const uint8_t* mask, float* angles, void* stream) {
+  if (n_env == 0) return RG_OK;   // empty batch: nothing to validate, nothing to launch
   RG_REQUIRE(ws && foot && angles && n_env >= 0, "rg_leg_ik");
-  if (n_env == 0) return RG_OK;
   ik_kernel<<<grid_for(4 * n_env, 256), 256, 0, (cudaStream_t)stream>>>((const RgRobotDev*)ws, n_env, foot, mask, angles);
   rg_count_launch();
   return rg_check_cuda(cudaGetLastError(), "ik_kernel launch");
 }
 
 extern "C" int rg_leg_fk(const void* ws, int n_env, const float* angles, float* foot, void* stream) {
+  if (n_env == 0) return RG_OK;   // empty batch: nothing to validate, nothing to launch
   RG_REQUIRE(ws && foot && angles && n_env >= 0, "rg_leg_fk");
-  if (n_env == 0) return RG_OK;
   fk_kernel<<<grid_for(4 * n_env, 256), 256, 0, (cudaStream_t)stream>>>((const RgRobotDev*)ws, n_env, angles, foot);
   rg_count_launch();
   return rg_check_cuda(cudaGetLastError(), "fk_kernel launch");
 }
 
 extern "C" int rg_force_to_torque(const void* ws, int n_env, const float* forces, const float* angles, float* torques, void* stream) {
+  if (n_env == 0) return RG_OK;   // empty batch: nothing to validate, nothing to launch
   RG_REQUIRE(ws && forces && angles && torques && n_env >= 0, "rg_force_to_torque");
-  if (n_env == 0) return RG_OK;
   torque_kernel<<<grid_for(4 * n_env, 256), 256, 0, (cudaStream_t)stream>>>((const RgRobotDev*)ws, n_env, forces, angles, torques);
   rg_count_launch();
   return rg_check_cuda(cudaGetLastError(), "torque_kernel launch");
@@ -598,22 +598,23 @@ extern "C" int rg_force_to_torque(const void* ws, int n_env, const float* forces
 
 extern "C" int rg_pack_hybrid_action(const void* ws, int n_env, const int32_t* desired, const float* swing_angles,
                                      const uint8_t* valid, const float* torques, float* action, void* stream) {
+  if (n_env == 0) return RG_OK;   // empty batch: nothing to validate, nothing to launch
   RG_REQUIRE(ws && desired && swing_angles && valid && torques && action && n_env >= 0, "rg_pack_hybrid_action");
-  if (n_env == 0) return RG_OK;
   pack_kernel<<<grid_for(4 * n_env, 256), 256, 0, (cudaStream_t)stream>>>((const RgRobotDev*)ws, n_env, desired, swing_angles, valid, torques, action);
   rg_count_launch();
   return rg_check_cuda(cudaGetLastError(), "pack_kernel launch");
 }
 
 extern "C" int rg_hybrid_motor_torque(int n_env, const float* action, const float* q, const float* qd, float* tau, void* stream) {
+  if (n_env == 0) return RG_OK;   // empty batch: nothing to validate, nothing to launch
   RG_REQUIRE(action && q && qd && tau && n_env >= 0, "rg_hybrid_motor_torque");
-  if (n_env == 0) return RG_OK;
   hybrid_motor_kernel<<<grid_for(12 * n_env, 256), 256, 0, (cudaStream_t)stream>>>(12 * n_env, action, q, qd, tau);
   rg_count_launch();
   return rg_check_cuda(cudaGetLastError(), "hybrid_motor_kernel launch");
 }
 
 extern "C" int rg_control_step(const void* mpc_ws, const void* robot_ws, int n_env, const rg_controller_state* s, void* stream) {
+  if (n_env == 0) return RG_OK;   // empty batch: nothing to validate, nothing to launch
   RG_REQUIRE(mpc_ws && robot_ws && s && n_env >= 0, "rg_control_step");
   RG_REQUIRE(s->time_since_reset && s->foot_contacts && s->base_velocity_world && s->base_orientation_xyzw && s->base_rpy &&
              s->base_rpy_rate && s->foot_positions_base && s->motor_angles && s->command, "rg_control_step inputs");
@@ -622,7 +623,6 @@ extern "C" int rg_control_step(const void* mpc_ws, const void* robot_ws, int n_e
              "rg_control_step state");
   RG_REQUIRE(s->desired_leg_state && s->leg_state && s->normalized_phase && s->mpc_contact_state && s->swing_foot_target &&
              s->com_velocity_body && s->contact_forces && s->motor_torques && s->action, "rg_control_step outputs");
-  if (n_env == 0) return RG_OK;
   cudaStream_t st = (cudaStream_t)stream;
   step_prologue_kernel<<<grid_for(n_env, 128), 128, 0, st>>>((const RgRobotDev*)robot_ws, n_env, *s);
   rg_count_launch();

@@ -24,7 +24,7 @@ RG_STATUS_POLISHED, RG_STATUS_IPM_CONVERGED, RG_STATUS_NO_STANCE, RG_STATUS_NUME
 
 # every symbol include/rg_cuda.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
-    "rg_mpc_default_params", "rg_workspace_bytes", "rg_mpc_setup", "rg_mpc_build_solve",
+    "rg_mpc_default_params", "rg_workspace_bytes", "rg_mpc_setup", "rg_mpc_release", "rg_mpc_build_solve",
     "rg_robot_calibrate_ik", "rg_robot_workspace_bytes", "rg_robot_setup",
     "rg_gait_step", "rg_com_velocity_update", "rg_swing_targets", "rg_leg_ik", "rg_leg_fk",
     "rg_force_to_torque", "rg_pack_hybrid_action", "rg_control_step", "rg_hybrid_motor_torque",
@@ -109,6 +109,7 @@ def load(build_if_missing: bool = False):
     lib.rg_mpc_default_params.argtypes = [POINTER(MpcParams), c_double, POINTER(c_double), c_double, c_int]
     lib.rg_workspace_bytes.argtypes = [c_int, c_int, c_int, POINTER(c_size_t)]
     lib.rg_mpc_setup.argtypes = [POINTER(MpcParams), c_void_p, c_size_t, c_void_p]
+    lib.rg_mpc_release.argtypes = [c_void_p]
     lib.rg_mpc_build_solve.argtypes = [c_void_p, c_int] + [c_void_p] * 10 + [c_void_p]
     lib.rg_robot_calibrate_ik.argtypes = [POINTER(RobotParams), POINTER(c_double)]
     lib.rg_robot_workspace_bytes.argtypes = [POINTER(c_size_t)]
@@ -197,6 +198,12 @@ class MpcWorkspace:
     def ptr(self):
         return c_void_p(self.buffer.data_ptr())
 
+    def __del__(self):
+        try:                       # the buffer's memory is about to return to the allocator
+            load().rg_mpc_release(c_void_p(self.buffer.data_ptr()))
+        except Exception:
+            pass
+
 
 class RobotWorkspace:
     """Device image of the robot model (leg chains, gait, gains) prepared by ``rg_robot_setup``."""
@@ -235,12 +242,12 @@ def mpc_build_solve(ws: MpcWorkspace, com_velocity_body, base_rpy, base_rpy_rate
         horizon_forces = torch.empty((n, ws.horizon, 12), dtype=torch.float32, device=dev)
     if solve_info is None and want_info:
         solve_info = torch.empty((n, 4), dtype=torch.int32, device=dev)
-    hf = None if horizon_forces is None else _ptr(horizon_forces.view(n, -1), torch.float32, (ws.horizon * 12,))
+    hf = None if horizon_forces is None else _ptr(horizon_forces.view(n, ws.horizon * 12), torch.float32, (ws.horizon * 12,))
     check(load().rg_mpc_build_solve(
         ws.ptr, n,
         _ptr(com_velocity_body, torch.float32, (3,)), _ptr(base_rpy, torch.float32, (3,)),
         _ptr(base_rpy_rate, torch.float32, (3,)), _ptr(foot_contact_state, torch.uint8, (4,)),
-        _ptr(foot_positions_base.view(n, -1), torch.float32, (12,)), _ptr(command, torch.float32, (3,)),
+        _ptr(foot_positions_base.view(n, 12), torch.float32, (12,)), _ptr(command, torch.float32, (3,)),
         _ptr(com_height, torch.float32, (), allow_none=True),
         _ptr(contact_forces, torch.float32, (12,)), hf,
         _ptr(solve_info, torch.int32, (4,), allow_none=True), current_stream_ptr()))
