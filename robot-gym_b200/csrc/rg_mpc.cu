@@ -55,6 +55,8 @@ struct Cfg {
   static constexpr int NKA = NA * (NA + 1) / 2;
   static constexpr int NKL = H * (H + 1) / 2;
   static constexpr int RPL = (N6 + 31) / 32;   // Psi rows per lane in the triangular sweeps
+  // resident CTAs per SM the register allocation is sized for (shared memory allows 9 / 2 at h = 10 / 20)
+  static constexpr int MIN_BLOCKS = H <= 5 ? 16 : (H <= 10 ? 8 : 2);
 };
 
 template <int H>
@@ -72,6 +74,7 @@ struct Smem {
   double k1[6];
   double k2lin[3];
   double qinv[H][9];               // (K1 + gamma_t K2)^-1 : 6 packed angular + 3 linear
+  double nblk[H][21];              // per time step: lower triangle of sum_legs B E^-1 B^T
   double red[3][8];
   int flag;
 };
@@ -116,74 +119,92 @@ __device__ __forceinline__ double quad_sum(double v) {   // sum over the 4 legs 
 }
 
 // ---- in-place Cholesky of the packed SPD matrix, one thread per row (left-looking) ------------
+// One barrier per column: every row thread recomputes the pivot of column j alongside its own dot
+// product (same row_j loads, one extra FMA per term) and takes rsqrt itself, so nobody waits for
+// the diagonal's owner.  The diagonal of Psi is left untouched in shared memory (other threads read
+// it as the original A[j][j]); the factor's diagonal lives in sm.rdiag as 1 / L[j][j], which is all
+// the triangular sweeps need.  __noinline__: one copy of the code, called from every phase.
 template <int H>
-__device__ __forceinline__ void cholesky_rows(Smem<H>& sm) {
+__device__ __noinline__ void cholesky_rows(Smem<H>& sm) {
   constexpr int N6 = Cfg<H>::N6;
   const int i = threadIdx.x;
-  double* row_i = sm.psi + tri(i < N6 ? i : 0, 0);
+  const bool row_ok = i < N6;
+  double* row_i = sm.psi + tri(row_ok ? i : 0, 0);
   if (i == 0) sm.flag = 0;   // published by the first barrier below
+#pragma unroll 1
   for (int j = 0; j < N6; ++j) {
-    double v = 0.0;
-    if (i >= j && i < N6) {
+    if (row_ok && i >= j) {
       const double* row_j = sm.psi + tri(j, 0);
-      double acc0 = row_i[j], acc1 = 0.0;
+      double a0 = row_i[j], a1 = 0.0, d0 = row_j[j], d1 = 0.0;
       int k = 0;
+#pragma unroll 2
       for (; k + 1 < j; k += 2) {
-        acc0 = fma(-row_i[k], row_j[k], acc0);
-        acc1 = fma(-row_i[k + 1], row_j[k + 1], acc1);
+        const double lj0 = row_j[k], lj1 = row_j[k + 1];
+        a0 = fma(-row_i[k], lj0, a0);
+        a1 = fma(-row_i[k + 1], lj1, a1);
+        d0 = fma(-lj0, lj0, d0);
+        d1 = fma(-lj1, lj1, d1);
       }
-      if (k < j) acc0 = fma(-row_i[k], row_j[k], acc0);
-      v = acc0 + acc1;
-      if (i == j) {
-        if (!(v > 0.0)) { sm.flag = 1; v = 1e-300; }
-        const double d = sqrt(v);
-        row_i[j] = d;
-        sm.rdiag[j] = 1.0 / d;
+      if (k < j) {
+        const double lj0 = row_j[k];
+        a0 = fma(-row_i[k], lj0, a0);
+        d0 = fma(-lj0, lj0, d0);
       }
+      double piv = d0 + d1;
+      if (!(piv > 0.0)) { if (i == j) sm.flag = 1; piv = 1e-300; }
+      const double r = rsqrt(piv);
+      if (i == j) sm.rdiag[j] = r;
+      else row_i[j] = (a0 + a1) * r;
     }
-    __syncthreads();
-    if (i > j && i < N6) row_i[j] = v * sm.rdiag[j];
     __syncthreads();
   }
 }
 
 // ---- Psi x = b with the factor, b/x in sm.avec; executed by warp 0 only ----------------------
+// Each lane owns rows lane, lane+32, ...; the pivot value travels by __shfl, no block barrier.
 template <int H>
-__device__ __forceinline__ void tri_solve_warp0(Smem<H>& sm) {
+__device__ __noinline__ void tri_solve_warp0(Smem<H>& sm) {
   constexpr int N6 = Cfg<H>::N6;
   constexpr int RPL = Cfg<H>::RPL;
   const int lane = threadIdx.x;   // caller guarantees threadIdx.x < 32
   double x[RPL];
+  int base[RPL];
 #pragma unroll
-  for (int r = 0; r < RPL; ++r) { const int i = lane + 32 * r; x[r] = i < N6 ? sm.avec[i] : 0.0; }
+  for (int r = 0; r < RPL; ++r) {
+    const int i = lane + 32 * r;
+    x[r] = i < N6 ? sm.avec[i] : 0.0;
+    base[r] = tri(i < N6 ? i : 0, 0);
+  }
   // forward: L y = b
 #pragma unroll
   for (int slot = 0; slot < RPL; ++slot) {
-    for (int jj = 0; jj < 32; ++jj) {
-      const int j = slot * 32 + jj;
-      if (j >= N6) break;
+    const int jend = N6 - 32 * slot < 32 ? N6 - 32 * slot : 32;
+#pragma unroll 1
+    for (int jj = 0; jj < jend; ++jj) {
+      const int j = 32 * slot + jj;
       double xj = x[slot] * sm.rdiag[j];
       xj = __shfl_sync(kFull, xj, jj);
       if (lane == jj) x[slot] = xj;
 #pragma unroll
-      for (int r = 0; r < RPL; ++r) {
+      for (int r = slot; r < RPL; ++r) {
         const int i = lane + 32 * r;
-        if (i > j && i < N6) x[r] = fma(-sm.psi[tri(i, j)], xj, x[r]);
+        if (i > j && i < N6) x[r] = fma(-sm.psi[base[r] + j], xj, x[r]);
       }
     }
   }
   // backward: L^T x = y
 #pragma unroll
   for (int slot = RPL - 1; slot >= 0; --slot) {
-    for (int jj = 31; jj >= 0; --jj) {
-      const int j = slot * 32 + jj;
-      if (j >= N6) continue;
+    const int jend = N6 - 32 * slot < 32 ? N6 - 32 * slot : 32;
+#pragma unroll 1
+    for (int jj = jend - 1; jj >= 0; --jj) {
+      const int j = 32 * slot + jj;
       double xj = x[slot] * sm.rdiag[j];
       xj = __shfl_sync(kFull, xj, jj);
       if (lane == jj) x[slot] = xj;
       const double* row_j = sm.psi + tri(j, 0);
 #pragma unroll
-      for (int r = 0; r < RPL; ++r) {
+      for (int r = 0; r <= slot; ++r) {
         const int i = lane + 32 * r;
         if (i < j) x[r] = fma(-row_j[i], xj, x[r]);
       }
@@ -193,23 +214,24 @@ __device__ __forceinline__ void tri_solve_warp0(Smem<H>& sm) {
   for (int r = 0; r < RPL; ++r) { const int i = lane + 32 * r; if (i < N6) sm.avec[i] = x[r]; }
 }
 
-// Psi := scale * K^-1 (packed), all threads
+// Row p of Psi := scale * K^-1[p][:] + (diagonal 6x6 block of sm.nblk), thread per row.
 template <int H>
-__device__ __forceinline__ void psi_init(Smem<H>& sm, double scale) {
+__device__ __forceinline__ void psi_build_rows(Smem<H>& sm) {
   constexpr int N6 = Cfg<H>::N6;
-  for (int p = threadIdx.x; p < N6; p += blockDim.x) {
+  const int p = threadIdx.x;
+  if (p < N6) {
     const int j = p / 6, c = p - 6 * j;
     double* row = sm.psi + tri(p, 0);
-    for (int q = 0; q <= p; ++q) {
-      const int k = q / 6, d = q - 6 * k;
-      double v = 0.0;
-      if (c < 3 && d < 3) {
-        const int a = 3 * j + c, b = 3 * k + d;   // a >= b because p >= q ... not always when j == k
-        v = a >= b ? sm.kinv_ang[tri(a, b)] : sm.kinv_ang[tri(b, a)];
-      } else if (c == d) {
-        v = sm.kinv_lin[c - 3][tri(j, k)];
+#pragma unroll 1
+    for (int k = 0; k <= j; ++k) {
+      const int dmax = k == j ? c : 5;
+      for (int d = 0; d <= dmax; ++d) {
+        double v = 0.0;
+        if (c < 3 && d < 3) v = sm.kinv_ang[tri(3 * j + c, 3 * k + d)];
+        else if (c == d) v = sm.kinv_lin[c - 3][tri(j, k)];
+        if (k == j) v += sm.nblk[j][c * (c + 1) / 2 + d];
+        row[6 * k + d] = v;
       }
-      row[q] = scale * v;
     }
   }
 }
@@ -266,8 +288,140 @@ __device__ __forceinline__ void g_mul(const double* f, const double* mu, double*
   c[4] = f[2];
 }
 
+// ---- per-thread context of a "block" thread: one (time step, leg) force triple ---------------------
+struct Blk {
+  double ba[9];       // A_leg = I_world^-1 [r]x   (zero for inactive threads)
+  double inv_mass;
+  double two_alpha;
+  int t, leg;
+  bool is_blk, act;   // act: this thread's leg is in stance
+};
+
+// out = P u for the triple held by this thread, P = 2 alpha I + W^T K W.  All threads call.
 template <int H>
-__global__ void __launch_bounds__(Cfg<H>::NT)
+__device__ __noinline__ void apply_p(Smem<H>& sm, const Blk& b, const double* uu, double* out) {
+  constexpr int N6 = Cfg<H>::N6;
+  const int tid = threadIdx.x;
+  double a6[6];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    a6[c] = b.ba[3 * c] * uu[0] + b.ba[3 * c + 1] * uu[1] + b.ba[3 * c + 2] * uu[2];
+    a6[3 + c] = b.inv_mass * uu[c];
+  }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) a6[c] = quad_sum(b.act ? a6[c] : 0.0);
+  if (b.is_blk && b.leg == 0) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) sm.avec[6 * b.t + c] = a6[c];
+  }
+  __syncthreads();
+  if (tid < N6) {
+    const int j = tid / 6, c = tid - 6 * j;
+    double s1 = 0.0;
+    for (int k = 0; k < H; ++k) s1 = fma(c1f(H, j, k), sm.avec[6 * k + c], s1);
+    double val = sm.k1[c] * s1;
+    if (c < 3) {
+      double s20 = 0.0, s21 = 0.0, s22 = 0.0;
+      for (int k = 0; k < H; ++k) {
+        const double cc = sm.c2tab[j * H + k];
+        s20 = fma(cc, sm.avec[6 * k + 0], s20);
+        s21 = fma(cc, sm.avec[6 * k + 1], s21);
+        s22 = fma(cc, sm.avec[6 * k + 2], s22);
+      }
+      val += sm.k2ang[3 * c] * s20 + sm.k2ang[3 * c + 1] * s21 + sm.k2ang[3 * c + 2] * s22;
+    } else {
+      double s2 = 0.0;
+      for (int k = 0; k < H; ++k) s2 = fma(sm.c2tab[j * H + k], sm.avec[6 * k + c], s2);
+      val += sm.k2lin[c - 3] * s2;
+    }
+    sm.kvec[tid] = val;
+  }
+  __syncthreads();
+  if (b.act) {
+    const double* kv = sm.kvec + 6 * b.t;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      out[d] = b.two_alpha * uu[d] + b.ba[d] * kv[0] + b.ba[3 + d] * kv[1] + b.ba[6 + d] * kv[2] + b.inv_mass * kv[3 + d];
+  } else {
+    out[0] = out[1] = out[2] = 0.0;
+  }
+}
+
+// Psi = K^-1 + sum_legs B M B^T (M = per-block symmetric 3x3, packed xx,yy,zz,xz,yz,xy), then its
+// Cholesky factor.  All threads call.
+template <int H>
+__device__ __noinline__ void factor_psi(Smem<H>& sm, const Blk& b, const double* m) {
+  double am[9];   // A M
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double a0 = b.ba[3 * a], a1 = b.ba[3 * a + 1], a2 = b.ba[3 * a + 2];
+    am[3 * a + 0] = a0 * m[0] + a1 * m[5] + a2 * m[3];
+    am[3 * a + 1] = a0 * m[5] + a1 * m[1] + a2 * m[4];
+    am[3 * a + 2] = a0 * m[3] + a1 * m[4] + a2 * m[2];
+  }
+  double n[21];   // lower triangle of the 6x6 block [[A M A^T, .],[M A^T / m, M / m^2]], row-major
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c <= r; ++c)
+      n[r * (r + 1) / 2 + c] = am[3 * r] * b.ba[3 * c] + am[3 * r + 1] * b.ba[3 * c + 1] + am[3 * r + 2] * b.ba[3 * c + 2];
+  const double mfull[9] = {m[0], m[5], m[3], m[5], m[1], m[4], m[3], m[4], m[2]};
+#pragma unroll
+  for (int r = 3; r < 6; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) n[r * (r + 1) / 2 + c] = am[3 * c + (r - 3)] * b.inv_mass;
+#pragma unroll
+    for (int c = 3; c <= r; ++c) n[r * (r + 1) / 2 + c] = mfull[3 * (r - 3) + (c - 3)] * b.inv_mass * b.inv_mass;
+  }
+#pragma unroll
+  for (int i = 0; i < 21; ++i) n[i] = quad_sum(b.act ? n[i] : 0.0);
+  if (b.is_blk && b.leg == 0) {
+#pragma unroll
+    for (int i = 0; i < 21; ++i) sm.nblk[b.t][i] = n[i];
+  }
+  __syncthreads();
+  psi_build_rows<H>(sm);
+  __syncthreads();
+  cholesky_rows<H>(sm);
+}
+
+// x = (E + W^T K W)^-1 rhs through the Woodbury identity, given the per-block E^-1 (packed) and the
+// factor of Psi = K^-1 + W E^-1 W^T.  All threads call.
+template <int H>
+__device__ __noinline__ void woodbury_solve(Smem<H>& sm, const Blk& b, const double* einv, const double* rhs, double* x) {
+  double w[3];
+  sym3_mul(einv, rhs, w);   // E^-1 rhs
+  double t6[6];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    t6[c] = b.ba[3 * c] * w[0] + b.ba[3 * c + 1] * w[1] + b.ba[3 * c + 2] * w[2];
+    t6[3 + c] = b.inv_mass * w[c];
+  }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) t6[c] = quad_sum(b.act ? t6[c] : 0.0);
+  if (b.is_blk && b.leg == 0) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) sm.avec[6 * b.t + c] = t6[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) tri_solve_warp0<H>(sm);
+  __syncthreads();
+  if (b.act) {
+    const double* v = sm.avec + 6 * b.t;
+    double bv[3], ebv[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) bv[d] = b.ba[d] * v[0] + b.ba[3 + d] * v[1] + b.ba[6 + d] * v[2] + b.inv_mass * v[3 + d];
+    sym3_mul(einv, bv, ebv);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x[d] = w[d] - ebv[d];
+  } else {
+    x[0] = x[1] = x[2] = 0.0;
+  }
+  __syncthreads();   // avec is reused by the next caller
+}
+
+template <int H>
+__global__ void __launch_bounds__(Cfg<H>::NT, Cfg<H>::MIN_BLOCKS)
 mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
                  const float* __restrict__ g_com_vel, const float* __restrict__ g_rpy,
                  const float* __restrict__ g_rpy_rate, const uint8_t* __restrict__ g_contacts,
@@ -470,139 +624,26 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   __syncthreads();
 
   // ---------------------------------------------------------------- per-block constants
-  double ba[9];   // A_leg
+  Blk blk;
 #pragma unroll
-  for (int i = 0; i < 9; ++i) ba[i] = active_blk ? sm.bang[leg][i] : 0.0;
+  for (int i = 0; i < 9; ++i) blk.ba[i] = active_blk ? sm.bang[leg][i] : 0.0;
+  blk.inv_mass = inv_mass;
+  blk.two_alpha = two_alpha;
+  blk.t = t_blk;
+  blk.leg = leg;
+  blk.is_blk = is_blk;
+  blk.act = active_blk;
   double q[3] = {0.0, 0.0, 0.0};
   if (active_blk) {
     const double* g6 = sm.gt + 6 * t_blk;
 #pragma unroll
-    for (int d = 0; d < 3; ++d) q[d] = ba[d] * g6[0] + ba[3 + d] * g6[1] + ba[6 + d] * g6[2] + inv_mass * g6[3 + d];
+    for (int d = 0; d < 3; ++d)
+      q[d] = blk.ba[d] * g6[0] + blk.ba[3 + d] * g6[1] + blk.ba[6 + d] * g6[2] + inv_mass * g6[3 + d];
   }
 
   // upper bounds hv (rows 0..4) and lower bounds (rows 5..9 as -g.f <= -l)
   const double hv_up[5] = {big_u, big_u, big_u, big_u, fzmax};
   const double lo_b[5] = {0.0, 0.0, 0.0, 0.0, fzmin};
-
-  // P u for the force triple held by this thread (all threads must call)
-  auto apply_p = [&](const double* uu, double* out) {
-    double a6[6];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      a6[c] = ba[3 * c] * uu[0] + ba[3 * c + 1] * uu[1] + ba[3 * c + 2] * uu[2];
-      a6[3 + c] = inv_mass * uu[c];
-    }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      a6[c] = quad_sum(active_blk ? a6[c] : 0.0);
-    }
-    if (is_blk && leg == 0) {
-#pragma unroll
-      for (int c = 0; c < 6; ++c) sm.avec[6 * t_blk + c] = a6[c];
-    }
-    __syncthreads();
-    if (tid < N6) {
-      const int j = tid / 6, c = tid % 6;
-      double s1 = 0.0;
-      for (int k = 0; k < H; ++k) s1 = fma(c1f(H, j, k), sm.avec[6 * k + c], s1);
-      double val = sm.k1[c] * s1;
-      if (c < 3) {
-        double s20 = 0.0, s21 = 0.0, s22 = 0.0;
-        for (int k = 0; k < H; ++k) {
-          const double cc = sm.c2tab[j * H + k];
-          s20 = fma(cc, sm.avec[6 * k + 0], s20);
-          s21 = fma(cc, sm.avec[6 * k + 1], s21);
-          s22 = fma(cc, sm.avec[6 * k + 2], s22);
-        }
-        val += sm.k2ang[3 * c] * s20 + sm.k2ang[3 * c + 1] * s21 + sm.k2ang[3 * c + 2] * s22;
-      } else {
-        double s2 = 0.0;
-        for (int k = 0; k < H; ++k) s2 = fma(sm.c2tab[j * H + k], sm.avec[6 * k + c], s2);
-        val += sm.k2lin[c - 3] * s2;
-      }
-      sm.kvec[tid] = val;
-    }
-    __syncthreads();
-    if (active_blk) {
-      const double* kv = sm.kvec + 6 * t_blk;
-#pragma unroll
-      for (int d = 0; d < 3; ++d)
-        out[d] = two_alpha * uu[d] + ba[d] * kv[0] + ba[3 + d] * kv[1] + ba[6 + d] * kv[2] + inv_mass * kv[3 + d];
-    } else {
-      out[0] = out[1] = out[2] = 0.0;
-    }
-  };
-
-  // Adds sum_legs (B M B^T) to the diagonal 6x6 blocks of Psi, M symmetric 3x3 packed
-  // (xx,yy,zz,xz,yz,xy); all threads call (shuffles), leg-0 lanes write.
-  auto add_n_blocks = [&](const double* m) {
-    // AM = A M  (3x3), N_aa = AM A^T (sym), N_al = AM / m, N_ll = M / m^2
-    double am[9];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const double a0 = ba[3 * a], a1 = ba[3 * a + 1], a2 = ba[3 * a + 2];
-      am[3 * a + 0] = a0 * m[0] + a1 * m[5] + a2 * m[3];
-      am[3 * a + 1] = a0 * m[5] + a1 * m[1] + a2 * m[4];
-      am[3 * a + 2] = a0 * m[3] + a1 * m[4] + a2 * m[2];
-    }
-    double n[21];   // lower triangle of the 6x6 block, row-major: (r,c) -> r(r+1)/2 + c
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int c = 0; c <= r; ++c)
-        n[r * (r + 1) / 2 + c] = am[3 * r] * ba[3 * c] + am[3 * r + 1] * ba[3 * c + 1] + am[3 * r + 2] * ba[3 * c + 2];
-    const double mfull[9] = {m[0], m[5], m[3], m[5], m[1], m[4], m[3], m[4], m[2]};
-#pragma unroll
-    for (int r = 3; r < 6; ++r) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) n[r * (r + 1) / 2 + c] = am[3 * c + (r - 3)] * inv_mass;   // N_la = (AM)^T / m
-#pragma unroll
-      for (int c = 3; c <= r; ++c) n[r * (r + 1) / 2 + c] = mfull[3 * (r - 3) + (c - 3)] * inv_mass * inv_mass;
-    }
-#pragma unroll
-    for (int i = 0; i < 21; ++i) n[i] = quad_sum(active_blk ? n[i] : 0.0);
-    if (is_blk && leg == 0) {
-      const int base = 6 * t_blk;
-#pragma unroll
-      for (int r = 0; r < 6; ++r)
-#pragma unroll
-        for (int c = 0; c <= r; ++c) sm.psi[tri(base + r, base + c)] += n[r * (r + 1) / 2 + c];
-    }
-  };
-
-  // Woodbury solve of (E + W^T K W) x = b given E^-1 blocks (einv) and the factor of Psi.
-  // All threads call.
-  auto woodbury = [&](const double* einv, const double* b, double* x) {
-    double w[3];
-    sym3_mul(einv, b, w);   // E^-1 b
-    double t6[6];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      t6[c] = ba[3 * c] * w[0] + ba[3 * c + 1] * w[1] + ba[3 * c + 2] * w[2];
-      t6[3 + c] = inv_mass * w[c];
-    }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) t6[c] = quad_sum(active_blk ? t6[c] : 0.0);
-    if (is_blk && leg == 0) {
-#pragma unroll
-      for (int c = 0; c < 6; ++c) sm.avec[6 * t_blk + c] = t6[c];
-    }
-    __syncthreads();
-    if (tid < 32) tri_solve_warp0<H>(sm);
-    __syncthreads();
-    if (active_blk) {
-      const double* v = sm.avec + 6 * t_blk;
-      double bv[3], ebv[3];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) bv[d] = ba[d] * v[0] + ba[3 + d] * v[1] + ba[6 + d] * v[2] + inv_mass * v[3 + d];
-      sym3_mul(einv, bv, ebv);
-#pragma unroll
-      for (int d = 0; d < 3; ++d) x[d] = w[d] - ebv[d];
-    } else {
-      x[0] = x[1] = x[2] = 0.0;
-    }
-    __syncthreads();   // avec is reused by the next caller
-  };
 
   // ---------------------------------------------------------------- interior point
   double u[3] = {0.0, 0.0, 0.0}, s[10], lam[10];
@@ -625,7 +666,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
       if (!active_blk) s[r] = 1.0;
-      lam[r] = active_blk ? 0.1 * qscale / s[r] : 0.0;
+      lam[r] = active_blk ? 0.1 * qscale / s[r] : 1.0;   // inactive threads carry harmless 1/1 pairs
     }
   }
   const double m_total = 10.0 * H * n_stance;
@@ -644,17 +685,27 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   double u_best[3] = {u[0], u[1], u[2]};
   int stall = 0;
   bool done = false;
+#pragma unroll 1
   for (int attempt = 0; attempt < 3 && !done; ++attempt) {
     bool converged = false, ipm_dead = false;
+#pragma unroll 1
     while (true) {
       double pu[3], rd[3], gl[3];
-      apply_p(u, pu);
+      apply_p<H>(sm, blk, u, pu);
       gt_mul(lam, mu, gl);
       double sl = 0.0, rdmax = 0.0, dmn = 0.0;
 #pragma unroll
       for (int d = 0; d < 3; ++d) { rd[d] = pu[d] + q[d] + gl[d]; rdmax = fmax(rdmax, fabs(rd[d])); }
+      // sl_r = s lam and its reciprocal: the only ten divisions of the iteration
+      double slr[10], is[10], il[10];
 #pragma unroll
-      for (int r = 0; r < 10; ++r) sl += s[r] * lam[r];
+      for (int r = 0; r < 10; ++r) {
+        slr[r] = s[r] * lam[r];
+        const double isl = 1.0 / slr[r];
+        is[r] = lam[r] * isl;     // 1 / s
+        il[r] = s[r] * isl;       // 1 / lam
+        sl += slr[r];
+      }
       if (!active_blk) { sl = 0.0; rdmax = 0.0; }
       block_reduce<C::NW>(sl, rdmax, dmn, sm.red);
       const double mu_c = sl / m_total;
@@ -680,83 +731,79 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       // block 3x3 parts and Psi
       double dd[5], einv[6];
 #pragma unroll
-      for (int r = 0; r < 5; ++r) dd[r] = lam[r] / s[r] + lam[5 + r] / s[5 + r];
+      for (int r = 0; r < 5; ++r) dd[r] = lam[r] * is[r] + lam[5 + r] * is[5 + r];
       block_inverse(dd, mu, two_alpha, einv);
-      psi_init<H>(sm, 1.0);
-      __syncthreads();
-      add_n_blocks(einv);
-      __syncthreads();
-      cholesky_rows<H>(sm);
+      factor_psi<H>(sm, blk, einv);
       if (sm.flag) { status |= RG_STATUS_NUMERIC; ipm_dead = true; break; }
 
-      // predictor: r_c = s lam  ->  rhs = -(P u + q)
-      double rhs[3], dxa[3];
+      // Mehrotra predictor (phase 0: r_c = s lam, rhs = -(P u + q)) and corrector (phase 1:
+      // r_c = s lam + ds_a dl_a - sigma mu, rhs = -r_d + G^T (r_c / s)); one copy of the solve code.
+      double wv[10], dx[3], c5[5];
+      double sigmu = 0.0;
 #pragma unroll
-      for (int d = 0; d < 3; ++d) rhs[d] = -(pu[d] + q[d]);
-      woodbury(einv, rhs, dxa);
-      double c5[5], pa[10];
-      g_mul(dxa, mu, c5);
-      double amax = 1.0;   // largest feasible affine step
-      double dsum = 0.0, dmx = 0.0;
+      for (int r = 0; r < 10; ++r) wv[r] = 0.0;
+#pragma unroll 1
+      for (int phase = 0; phase < 2; ++phase) {
+        double rhs[3];
+        if (phase == 0) {
 #pragma unroll
-      for (int r = 0; r < 10; ++r) {
-        const double ds = r < 5 ? -c5[r] : c5[r - 5];
-        const double dl = -lam[r] - lam[r] * ds / s[r];
-        pa[r] = ds * dl;
-        if (active_blk) {
-          if (ds < 0.0) amax = fmin(amax, -s[r] / ds);
-          if (dl < 0.0) amax = fmin(amax, -lam[r] / dl);
+          for (int d = 0; d < 3; ++d) rhs[d] = -(pu[d] + q[d]);
+        } else {
+          double gw[3];
+          gt_mul(wv, mu, gw);
+#pragma unroll
+          for (int d = 0; d < 3; ++d) rhs[d] = -rd[d] + gw[d];
+        }
+        woodbury_solve<H>(sm, blk, einv, rhs, dx);
+        g_mul(dx, mu, c5);
+        if (phase == 0) {
+          // x_r = ds_r / s_r ; dl_r / lam_r = -1 - x_r: the largest feasible affine step is 1 / max(-x, 1 + x)
+          double tmax = 1.0, dsum = 0.0, dmn2 = 0.0;
+          double xr[10];
+#pragma unroll
+          for (int r = 0; r < 10; ++r) {
+            xr[r] = (r < 5 ? -c5[r] : c5[r - 5]) * is[r];
+            if (active_blk) tmax = fmax(tmax, fmax(-xr[r], 1.0 + xr[r]));
+          }
+          block_reduce<C::NW>(dsum, tmax, dmn2, sm.red);
+          const double amax = 1.0 / tmax;
+          double mu_aff = 0.0;
+#pragma unroll
+          for (int r = 0; r < 10; ++r) {
+            mu_aff += slr[r] * (1.0 + amax * xr[r]) * (1.0 - amax * (1.0 + xr[r]));
+            wv[r] = -slr[r] * xr[r] * (1.0 + xr[r]);          // ds_a dl_a
+          }
+          if (!active_blk) mu_aff = 0.0;
+          double dmx3 = 0.0, dmn3 = 0.0;
+          block_reduce<C::NW>(mu_aff, dmx3, dmn3, sm.red);
+          mu_aff /= m_total;
+          const double ratio = mu_aff / mu_c;
+          sigmu = ratio * ratio * ratio * mu_c;
+#pragma unroll
+          for (int r = 0; r < 10; ++r) wv[r] = (slr[r] + wv[r] - sigmu) * is[r];   // r_c / s
         }
       }
-      block_reduce<C::NW>(dsum, dmx, amax, sm.red);
-      double mu_aff = 0.0;
+      // step to the boundary: -ds/s = -y, -dl/lam = w/lam + y with y = ds/s
+      double tmax = 0.0, dsum = 0.0, dmn2 = 0.0;
+      double yr[10];
 #pragma unroll
       for (int r = 0; r < 10; ++r) {
-        const double ds = r < 5 ? -c5[r] : c5[r - 5];
-        const double dl = -lam[r] - lam[r] * ds / s[r];
-        mu_aff += (s[r] + amax * ds) * (lam[r] + amax * dl);
+        yr[r] = (r < 5 ? -c5[r] : c5[r - 5]) * is[r];
+        if (active_blk) tmax = fmax(tmax, fmax(-yr[r], wv[r] * il[r] + yr[r]));
       }
-      if (!active_blk) mu_aff = 0.0;
-      {
-        double dmx2 = 0.0, dmn2 = 0.0;
-        block_reduce<C::NW>(mu_aff, dmx2, dmn2, sm.red);
-      }
-      mu_aff /= m_total;
-      const double sig = (mu_aff / mu_c) * (mu_aff / mu_c) * (mu_aff / mu_c);
-      const double sigmu = sig * mu_c;
-
-      // corrector: r_c = s lam + ds_a dl_a - sigma mu ; rhs = -rd + G^T (r_c / s)
-      double wv[10], gw[3], dx[3];
+      block_reduce<C::NW>(dsum, tmax, dmn2, sm.red);
+      const double step = tmax > 0.99 ? 0.99 / tmax : 1.0;
+      if (active_blk) {
 #pragma unroll
-      for (int r = 0; r < 10; ++r) wv[r] = (s[r] * lam[r] + pa[r] - sigmu) / s[r];
-      gt_mul(wv, mu, gw);
-#pragma unroll
-      for (int d = 0; d < 3; ++d) rhs[d] = -rd[d] + gw[d];
-      woodbury(einv, rhs, dx);
-      g_mul(dx, mu, c5);
-      double step = 1e30;
-#pragma unroll
-      for (int r = 0; r < 10; ++r) {
-        const double ds = r < 5 ? -c5[r] : c5[r - 5];
-        const double dl = (-(s[r] * lam[r] + pa[r] - sigmu) - lam[r] * ds) / s[r];
-        if (active_blk) {
-          if (ds < 0.0) step = fmin(step, -s[r] / ds);
-          if (dl < 0.0) step = fmin(step, -lam[r] / dl);
-        }
-      }
-      block_reduce<C::NW>(dsum, dmx, step, sm.red);
-      step = fmin(1.0, 0.99 * step);
-#pragma unroll
-      for (int r = 0; r < 10; ++r) {
-        const double ds = r < 5 ? -c5[r] : c5[r - 5];
-        const double dl = (-(s[r] * lam[r] + pa[r] - sigmu) - lam[r] * ds) / s[r];
-        if (active_blk) {
+        for (int r = 0; r < 10; ++r) {
+          const double ds = yr[r] * s[r];
+          const double dl = -wv[r] - lam[r] * yr[r];
           s[r] += step * ds;
           lam[r] += step * dl;
         }
-      }
 #pragma unroll
-      for (int d = 0; d < 3; ++d) u[d] += step * dx[d];
+        for (int d = 0; d < 3; ++d) u[d] += step * dx[d];
+      }
     }
     if (converged) status |= RG_STATUS_IPM_CONVERGED; else status &= ~RG_STATUS_IPM_CONVERGED;
     if (max_polish <= 0) {
@@ -772,6 +819,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     bool polished = false;
     double up[3] = {0.0, 0.0, 0.0};
     const int round_budget = max_polish << attempt;   // 3, 6, 12: later attempts start from a sharper guess
+#pragma unroll 1
     for (int round = 0; round < round_budget; ++round) {
       ++polish_rounds;
       // --- per block: orthonormal basis of the active normals (<= 3), null-space basis Z, u0
@@ -781,7 +829,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       int rows[3] = {-1, -1, -1};
       int na = 0;
       if (active_blk) {
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < 10; ++r) {
           if (!((act >> r) & 1u) || na >= 3) continue;
           const int rw = r < 5 ? r : r - 5;
@@ -795,7 +843,8 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
           }
           const double nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
           if (nrm < 1e-9) { act &= ~(1u << r); continue; }   // dependent normal: drop
-          e[na][0] = a[0] / nrm; e[na][1] = a[1] / nrm; e[na][2] = a[2] / nrm;
+          const double inrm = 1.0 / nrm;
+          e[na][0] = a[0] * inrm; e[na][1] = a[1] * inrm; e[na][2] = a[2] * inrm;
           for (int k = 0; k < na; ++k) rr[k][na] = coef[k];
           rr[na][na] = nrm;
           bt[na] = target;
@@ -803,105 +852,54 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
           ++na;
         }
         // rows beyond the third independent one cannot be held: drop them from the guess
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < 10; ++r) {
           if (((act >> r) & 1u) && r != rows[0] && r != rows[1] && r != rows[2]) act &= ~(1u << r);
         }
       }
       // particular solution u0 = sum_k c_k e_k with a_i . u0 = b_i
       double cpar[3] = {0, 0, 0};
+#pragma unroll 1
       for (int i = 0; i < na; ++i) {
         double v = bt[i];
         for (int k = 0; k < i; ++k) v -= rr[k][i] * cpar[k];
         cpar[i] = v / rr[i][i];
       }
       double u0[3] = {0, 0, 0};
+#pragma unroll 1
       for (int k = 0; k < na; ++k) { u0[0] += cpar[k] * e[k][0]; u0[1] += cpar[k] * e[k][1]; u0[2] += cpar[k] * e[k][2]; }
-      // null-space basis z[0..nf)
-      double z[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-      const int nf = active_blk ? 3 - na : 0;
-      if (active_blk) {
-        if (na == 0) { z[0][0] = 1.0; z[1][1] = 1.0; z[2][2] = 1.0; }
-        else if (na == 1) {
-          // two unit vectors orthogonal to e[0]
-          const double ax = fabs(e[0][0]), ay = fabs(e[0][1]), az = fabs(e[0][2]);
-          double h3[3] = {0, 0, 0};
-          if (ax <= ay && ax <= az) h3[0] = 1.0; else if (ay <= az) h3[1] = 1.0; else h3[2] = 1.0;
-          double v0 = e[0][1] * h3[2] - e[0][2] * h3[1], v1 = e[0][2] * h3[0] - e[0][0] * h3[2], v2 = e[0][0] * h3[1] - e[0][1] * h3[0];
-          const double n1 = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
-          z[0][0] = v0 / n1; z[0][1] = v1 / n1; z[0][2] = v2 / n1;
-          z[1][0] = e[0][1] * z[0][2] - e[0][2] * z[0][1];
-          z[1][1] = e[0][2] * z[0][0] - e[0][0] * z[0][2];
-          z[1][2] = e[0][0] * z[0][1] - e[0][1] * z[0][0];
-        } else if (na == 2) {
-          z[0][0] = e[0][1] * e[1][2] - e[0][2] * e[1][1];
-          z[0][1] = e[0][2] * e[1][0] - e[0][0] * e[1][2];
-          z[0][2] = e[0][0] * e[1][1] - e[0][1] * e[1][0];
-        }
+      // projector onto the free directions  M = I - sum_k e_k e_k^T, packed (xx,yy,zz,xz,yz,xy),
+      // scaled by 1 / (2 alpha): this is the "E^-1" of the equality-constrained Newton system
+      double mproj[6] = {1.0, 1.0, 1.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+      for (int k = 0; k < na; ++k) {
+        mproj[0] -= e[k][0] * e[k][0]; mproj[1] -= e[k][1] * e[k][1]; mproj[2] -= e[k][2] * e[k][2];
+        mproj[3] -= e[k][0] * e[k][2]; mproj[4] -= e[k][1] * e[k][2]; mproj[5] -= e[k][0] * e[k][1];
       }
-      // M = Z Z^T (projector onto the free directions), packed (xx,yy,zz,xz,yz,xy)
-      double mproj[6] = {0, 0, 0, 0, 0, 0};
-      for (int k = 0; k < nf; ++k) {
-        mproj[0] += z[k][0] * z[k][0]; mproj[1] += z[k][1] * z[k][1]; mproj[2] += z[k][2] * z[k][2];
-        mproj[3] += z[k][0] * z[k][2]; mproj[4] += z[k][1] * z[k][2]; mproj[5] += z[k][0] * z[k][1];
-      }
-      // Psi_p = 2 alpha K^-1 + sum (B Z)(B Z)^T
-      psi_init<H>(sm, two_alpha);
-      __syncthreads();
-      add_n_blocks(mproj);
-      __syncthreads();
-      cholesky_rows<H>(sm);
+      if (na == 3 || !active_blk) { mproj[0] = mproj[1] = mproj[2] = mproj[3] = mproj[4] = mproj[5] = 0.0; }
+      const double inv2a = 1.0 / two_alpha;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) mproj[i] *= inv2a;
+      factor_psi<H>(sm, blk, mproj);
       if (sm.flag) { status |= RG_STATUS_NUMERIC; ipm_dead = true; break; }
 
       // two passes: the solve and one step of iterative refinement
 #pragma unroll
       for (int d = 0; d < 3; ++d) up[d] = u0[d];
+#pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {
-        double pu[3], gr[3];
-        apply_p(up, pu);
+        double pu[3], ng[3], dx[3];
+        apply_p<H>(sm, blk, up, pu);
 #pragma unroll
-        for (int d = 0; d < 3; ++d) gr[d] = pu[d] + q[d];
-        // projected gradient r = Z Z^T gr ; x = -(1/2a) [ r - Z Z^T B^T Psi_p^-1 B r ]
-        // = woodbury with "E^-1" := Z Z^T / (2 alpha) ... expressed through the projector:
-        double rproj[3], dx[3];
-        sym3_mul(mproj, gr, rproj);
-        // reuse woodbury(): E^-1 = mproj/(2a)  =>  Psi = K^-1 + B mproj B^T / (2a); we factorised
-        // 2a K^-1 + B mproj B^T = 2a * that, so scale the right-hand side instead.
-        double w[3] = {rproj[0], rproj[1], rproj[2]};
-        double t6[6];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          t6[c] = ba[3 * c] * w[0] + ba[3 * c + 1] * w[1] + ba[3 * c + 2] * w[2];
-          t6[3 + c] = inv_mass * w[c];
-        }
-#pragma unroll
-        for (int c = 0; c < 6; ++c) t6[c] = quad_sum(active_blk ? t6[c] : 0.0);
-        if (is_blk && leg == 0) {
-#pragma unroll
-          for (int c = 0; c < 6; ++c) sm.avec[6 * t_blk + c] = t6[c];
-        }
-        __syncthreads();
-        if (tid < 32) tri_solve_warp0<H>(sm);
-        __syncthreads();
-        if (active_blk) {
-          const double* v = sm.avec + 6 * t_blk;
-          double bv[3], pbv[3];
-#pragma unroll
-          for (int d = 0; d < 3; ++d) bv[d] = ba[d] * v[0] + ba[3 + d] * v[1] + ba[6 + d] * v[2] + inv_mass * v[3 + d];
-          sym3_mul(mproj, bv, pbv);
-#pragma unroll
-          for (int d = 0; d < 3; ++d) dx[d] = -(rproj[d] - pbv[d]) / two_alpha;
-        } else {
-          dx[0] = dx[1] = dx[2] = 0.0;
-        }
-        __syncthreads();
+        for (int d = 0; d < 3; ++d) ng[d] = -(pu[d] + q[d]);
+        woodbury_solve<H>(sm, blk, mproj, ng, dx);
 #pragma unroll
         for (int d = 0; d < 3; ++d) up[d] += dx[d];
       }
 
       // --- verify: primal feasibility of the rows left out, multiplier signs of the rows held
       double pu[3], gr[3];
-      apply_p(up, pu);
+      apply_p<H>(sm, blk, up, pu);
 #pragma unroll
       for (int d = 0; d < 3; ++d) gr[d] = pu[d] + q[d];
       unsigned act_new = act;
@@ -916,11 +914,13 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
         }
         // multipliers: sum_i y_i a_i = -gr on span(e)
         double y[3] = {0, 0, 0};
+#pragma unroll 1
         for (int i = na - 1; i >= 0; --i) {
           double v = -(gr[0] * e[i][0] + gr[1] * e[i][1] + gr[2] * e[i][2]);
           for (int k = i + 1; k < na; ++k) v -= rr[i][k] * y[k];
           y[i] = v / rr[i][i];
         }
+#pragma unroll 1
         for (int i = 0; i < na; ++i) {
           // upper-bound rows need y >= 0, lower-bound rows y <= 0
           const double ysgn = rows[i] < 5 ? y[i] : -y[i];
@@ -930,12 +930,14 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       double changed = (act_new != act) ? 1.0 : 0.0, dmx = 0.0, dmn = 0.0;
       block_reduce<C::NW>(changed, dmx, dmn, sm.red);
       act = act_new;
+#ifdef RG_DEBUG_TRACE
       {
         double cnt = (double)__popc(act), dmx2 = 0.0, dmn2 = 0.0;
         block_reduce<C::NW>(cnt, dmx2, dmn2, sm.red);
         RG_TRACE(4 * trace_n + 0, -1.0); RG_TRACE(4 * trace_n + 1, changed); RG_TRACE(4 * trace_n + 2, cnt); RG_TRACE(4 * trace_n + 3, (double)round);
         ++trace_n;
       }
+#endif
       if (changed == 0.0) { polished = true; break; }
     }
     if (polished) {
@@ -988,6 +990,9 @@ int launch_h(const RgMpcDev* ws, int n_env, const float* com_vel, const float* r
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(mpc_solve_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return rg_check_cuda(e, "cudaFuncSetAttribute(mpc_solve_kernel)");
+    // the default carveout leaves room for only ~5 CTAs of 24 KB: ask for the full 227 KB of shared memory
+    e = cudaFuncSetAttribute(mpc_solve_kernel<H>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return rg_check_cuda(e, "cudaFuncSetAttribute(carveout)");
     attr_set = true;
   }
   mpc_solve_kernel<H><<<n_env, Cfg<H>::NT, smem, stream>>>(ws, n_env, com_vel, rpy, rpy_rate, contacts, feet, command,
