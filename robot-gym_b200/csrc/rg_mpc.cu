@@ -385,10 +385,11 @@ __device__ __noinline__ void factor_psi(Smem<H>& sm, const Blk& b, const double*
   cholesky_rows<H>(sm);
 }
 
-// x = (E + W^T K W)^-1 rhs through the Woodbury identity, given the per-block E^-1 (packed) and the
-// factor of Psi = K^-1 + W E^-1 W^T.  All threads call.
+// First half of x = (E + W^T K W)^-1 rhs through the Woodbury identity: given the per-block E^-1
+// (packed) and the factor of Psi = K^-1 + W E^-1 W^T it returns  b' = rhs - W^T v,
+// v = Psi^-1 W E^-1 rhs; the caller finishes with the block solve x = E^-1 b'.  All threads call.
 template <int H>
-__device__ __noinline__ void woodbury_solve(Smem<H>& sm, const Blk& b, const double* einv, const double* rhs, double* x) {
+__device__ __noinline__ void woodbury_solve(Smem<H>& sm, const Blk& b, const double* einv, const double* rhs, double* bprime) {
   double w[3];
   sym3_mul(einv, rhs, w);   // E^-1 rhs
   double t6[6];
@@ -408,16 +409,73 @@ __device__ __noinline__ void woodbury_solve(Smem<H>& sm, const Blk& b, const dou
   __syncthreads();
   if (b.act) {
     const double* v = sm.avec + 6 * b.t;
-    double bv[3], ebv[3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) bv[d] = b.ba[d] * v[0] + b.ba[3 + d] * v[1] + b.ba[6 + d] * v[2] + b.inv_mass * v[3 + d];
-    sym3_mul(einv, bv, ebv);
-#pragma unroll
-    for (int d = 0; d < 3; ++d) x[d] = w[d] - ebv[d];
+    for (int d = 0; d < 3; ++d)
+      bprime[d] = rhs[d] - (b.ba[d] * v[0] + b.ba[3 + d] * v[1] + b.ba[6 + d] * v[2] + b.inv_mass * v[3 + d]);
   } else {
-    x[0] = x[1] = x[2] = 0.0;
+    bprime[0] = bprime[1] = bprime[2] = 0.0;
   }
   __syncthreads();   // avec is reused by the next caller
+}
+
+// ---- accurate block solve for the interior point -------------------------------------------------
+// E = 2 alpha I + sum_r D_r g_r g_r^T.  Solving E dx = b' with an explicit 3x3 inverse loses the
+// constraint-space products c_r = g_r . dx of strongly active rows (D_r ~ 1e10) to cancellation,
+// and those are exactly what the slack update ds = -/+ c needs.  The 5x5 form
+//     S z = G b',  S = 2 alpha D^-1 + G G^T,   c = D^-1 z,   dx = (b' - G^T z) / (2 alpha)
+// delivers c without cancellation.  chol5 factors S in registers.
+struct Chol5 { double l[15]; };   // lower triangle, row-major; diagonal entries hold 1 / L[i][i]
+
+__device__ __forceinline__ void chol5_factor(const double* mu, const double* inv_d, double two_alpha, Chol5& c) {
+  // Gram matrix of the rows (-1,0,mu0) (1,0,mu1) (0,-1,mu2) (0,1,mu3) (0,0,1)
+  double a[15];
+  a[0] = 1.0 + mu[0] * mu[0];
+  a[1] = -1.0 + mu[0] * mu[1]; a[2] = 1.0 + mu[1] * mu[1];
+  a[3] = mu[0] * mu[2]; a[4] = mu[1] * mu[2]; a[5] = 1.0 + mu[2] * mu[2];
+  a[6] = mu[0] * mu[3]; a[7] = mu[1] * mu[3]; a[8] = -1.0 + mu[2] * mu[3]; a[9] = 1.0 + mu[3] * mu[3];
+  a[10] = mu[0]; a[11] = mu[1]; a[12] = mu[2]; a[13] = mu[3]; a[14] = 1.0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) a[i * (i + 1) / 2 + i] += two_alpha * inv_d[i];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    double d = a[j * (j + 1) / 2 + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d = fma(-c.l[j * (j + 1) / 2 + k], c.l[j * (j + 1) / 2 + k], d);
+    const double r = rsqrt(fmax(d, 1e-300));
+    c.l[j * (j + 1) / 2 + j] = r;
+#pragma unroll
+    for (int i = j + 1; i < 5; ++i) {
+      double v = a[i * (i + 1) / 2 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v = fma(-c.l[i * (i + 1) / 2 + k], c.l[j * (j + 1) / 2 + k], v);
+      c.l[i * (i + 1) / 2 + j] = v * r;
+    }
+  }
+}
+
+// z = S^-1 (G b'), c5 = D^-1 z (= G dx), dx = (b' - G^T z) / (2 alpha)
+__device__ __forceinline__ void chol5_block_solve(const Chol5& c, const double* mu, const double* inv_d, double two_alpha,
+                                                  const double* bprime, double* dx, double* c5) {
+  double z[5];
+  g_mul(bprime, mu, z);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+#pragma unroll
+    for (int k = 0; k < i; ++k) z[i] = fma(-c.l[i * (i + 1) / 2 + k], z[k], z[i]);
+    z[i] *= c.l[i * (i + 1) / 2 + i];
+  }
+#pragma unroll
+  for (int i = 4; i >= 0; --i) {
+#pragma unroll
+    for (int k = i + 1; k < 5; ++k) z[i] = fma(-c.l[k * (k + 1) / 2 + i], z[k], z[i]);
+    z[i] *= c.l[i * (i + 1) / 2 + i];
+  }
+  const double inv2a = 1.0 / two_alpha;
+  dx[0] = (bprime[0] - (z[1] - z[0])) * inv2a;
+  dx[1] = (bprime[1] - (z[3] - z[2])) * inv2a;
+  dx[2] = (bprime[2] - (mu[0] * z[0] + mu[1] * z[1] + mu[2] * z[2] + mu[3] * z[3] + z[4])) * inv2a;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) c5[i] = z[i] * inv_d[i];
 }
 
 template <int H>
@@ -647,7 +705,8 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 
   // ---------------------------------------------------------------- interior point
   double u[3] = {0.0, 0.0, 0.0}, s[10], lam[10];
-  const double fz0 = sqrt(fmax(fzmin, 1e-3 * fzmax) * fzmax);
+  // strictly feasible start: every stance foot carries its share of the weight
+  const double fz0 = fmin(0.5 * (fzmin + fzmax), fmax(2.0 * fzmin, ws->gravity / (inv_mass * n_stance)));
   u[2] = active_blk ? fz0 : 0.0;
   double qmax = active_blk ? fmax(fabs(q[0]), fmax(fabs(q[1]), fabs(q[2]))) : 0.0;
   {
@@ -666,7 +725,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
       if (!active_blk) s[r] = 1.0;
-      lam[r] = active_blk ? 0.1 * qscale / s[r] : 1.0;   // inactive threads carry harmless 1/1 pairs
+      lam[r] = active_blk ? 0.01 * qscale / s[r] : 1.0;   // inactive threads carry harmless 1/1 pairs
     }
   }
   const double m_total = 10.0 * H * n_stance;
@@ -722,7 +781,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       prev_res = res;
       // dead: budget spent, stalled at the numerical floor, NaN, or diverging (deep iterates lose the
       // tiny slacks of active rows to cancellation in ds = -G dx)
-      if (iters >= max_iters || stall >= 4 || !(res == res) || (res > 1e3 * best_res && best_res < 1e-6)) {
+      if (iters >= max_iters || stall >= 4 || !(res == res) || res > 1e3 * best_res) {
         ipm_dead = true;
         break;
       }
@@ -733,6 +792,11 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 #pragma unroll
       for (int r = 0; r < 5; ++r) dd[r] = lam[r] * is[r] + lam[5 + r] * is[5 + r];
       block_inverse(dd, mu, two_alpha, einv);
+      double inv_d[5];
+#pragma unroll
+      for (int r = 0; r < 5; ++r) inv_d[r] = 1.0 / dd[r];
+      Chol5 ch;
+      chol5_factor(mu, inv_d, two_alpha, ch);
       factor_psi<H>(sm, blk, einv);
       if (sm.flag) { status |= RG_STATUS_NUMERIC; ipm_dead = true; break; }
 
@@ -754,8 +818,9 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 #pragma unroll
           for (int d = 0; d < 3; ++d) rhs[d] = -rd[d] + gw[d];
         }
-        woodbury_solve<H>(sm, blk, einv, rhs, dx);
-        g_mul(dx, mu, c5);
+        double bprime[3];
+        woodbury_solve<H>(sm, blk, einv, rhs, bprime);
+        chol5_block_solve(ch, mu, inv_d, two_alpha, bprime, dx, c5);   // c5 = G dx without cancellation
         if (phase == 0) {
           // x_r = ds_r / s_r ; dl_r / lam_r = -1 - x_r: the largest feasible affine step is 1 / max(-x, 1 + x)
           double tmax = 1.0, dsum = 0.0, dmn2 = 0.0;
@@ -792,7 +857,10 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
         if (active_blk) tmax = fmax(tmax, fmax(-yr[r], wv[r] * il[r] + yr[r]));
       }
       block_reduce<C::NW>(dsum, tmax, dmn2, sm.red);
-      const double step = tmax > 0.99 ? 0.99 / tmax : 1.0;
+      // fraction to the boundary: 0.99 far out, 0.999 once both residuals are small (a step closer to 1
+      // collapses the slacks while the dual residual is still finite and de-centres the iterate)
+      const double tau = res < 1e-3 ? 0.999 : 0.99;
+      const double step = tmax > tau ? tau / tmax : 1.0;
       if (active_blk) {
 #pragma unroll
         for (int r = 0; r < 10; ++r) {
@@ -815,10 +883,11 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     // -------------------------------------------------------------- active-set polish
     unsigned act = 0;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) if (active_blk && lam[r] > s[r]) act |= 1u << r;
+    for (int r = 0; r < 10; ++r) if (active_blk && lam[r] > 0.03 * s[r]) act |= 1u << r;
     bool polished = false;
     double up[3] = {0.0, 0.0, 0.0};
-    const int round_budget = max_polish << attempt;   // 3, 6, 12: later attempts start from a sharper guess
+    // 3, 6, 12 rounds: later attempts start from a sharper guess; a dead interior point gets the full budget
+    const int round_budget = ipm_dead ? (max_polish << 2) : (max_polish << attempt);
 #pragma unroll 1
     for (int round = 0; round < round_budget; ++round) {
       ++polish_rounds;
@@ -892,7 +961,9 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
         apply_p<H>(sm, blk, up, pu);
 #pragma unroll
         for (int d = 0; d < 3; ++d) ng[d] = -(pu[d] + q[d]);
-        woodbury_solve<H>(sm, blk, mproj, ng, dx);
+        double bprime[3];
+        woodbury_solve<H>(sm, blk, mproj, ng, bprime);
+        sym3_mul(mproj, bprime, dx);
 #pragma unroll
         for (int d = 0; d < 3; ++d) up[d] += dx[d];
       }
