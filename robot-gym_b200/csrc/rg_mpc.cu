@@ -358,7 +358,7 @@ struct Blk {
 
 // out = P u for the triple held by this thread, P = 2 alpha I + W^T K W.  All threads call.
 template <int H>
-__device__ __noinline__ void apply_p(Smem<H>& sm, const Blk& b, const double* uu, double* out) {
+__device__ __forceinline__ void apply_p(Smem<H>& sm, const Blk& b, const double* uu, double* out) {
   constexpr int N6 = Cfg<H>::N6;
   const int tid = threadIdx.x;
   double a6[6];
@@ -409,7 +409,7 @@ __device__ __noinline__ void apply_p(Smem<H>& sm, const Blk& b, const double* uu
 // Psi = K^-1 + sum_legs B M B^T (M = per-block symmetric 3x3, packed xx,yy,zz,xz,yz,xy), then its
 // Cholesky factor.  All threads call.
 template <int H>
-__device__ __noinline__ void factor_psi(Smem<H>& sm, const Blk& b, const double* m) {
+__device__ __forceinline__ void factor_psi(Smem<H>& sm, const Blk& b, const double* m) {
   double am[9];   // A M
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
@@ -448,7 +448,7 @@ __device__ __noinline__ void factor_psi(Smem<H>& sm, const Blk& b, const double*
 // (packed) and the factor of Psi = K^-1 + W E^-1 W^T it returns  b' = rhs - W^T v,
 // v = Psi^-1 W E^-1 rhs; the caller finishes with the block solve x = E^-1 b'.  All threads call.
 template <int H>
-__device__ __noinline__ void woodbury_solve(Smem<H>& sm, const Blk& b, const double* einv, const double* rhs, double* bprime) {
+__device__ __forceinline__ void woodbury_solve(Smem<H>& sm, const Blk& b, const double* einv, const double* rhs, double* bprime) {
   double w[3];
   sym3_mul(einv, rhs, w);   // E^-1 rhs
   double t6[6];
