@@ -16,7 +16,7 @@ PKG_ROOT = os.path.abspath(os.path.join(_HERE, "..", ".."))          # robot-gym
 REPO_ROOT = os.path.abspath(os.path.join(PKG_ROOT, ".."))
 CSRC = os.path.join(PKG_ROOT, "csrc")
 INCLUDE = os.path.join(REPO_ROOT, "include")
-LIB_PATH = os.path.join(_HERE, "librg_cuda.so")
+LIB_PATH = os.environ.get("RG_CUDA_LIB") or os.path.join(_HERE, "librg_cuda.so")   # override: A/B builds while tuning
 STAMP_PATH = LIB_PATH + ".stamp"
 
 SOURCES = ("rg_api.cu", "rg_mpc.cu", "rg_robot.cu")
