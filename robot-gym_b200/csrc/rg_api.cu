@@ -245,6 +245,22 @@ extern "C" int rg_mpc_setup(const rg_mpc_params* p, void* workspace, size_t work
     rg_set_error("horizon table factorisation failed");
     return RG_ERR_SINGULAR;
   }
+  {
+    // env-independent tables: c2 and the inverse of the three linear channels of K,
+    // K_lin,c = 2 dt^2 w_v,c c1 + 2 dt^4 w_p,c c2  =>  K_lin,c^-1 = U diag(1 / (k1 + gamma_t k2)) U^T
+    const int hz = p->horizon;
+    const double dt2 = p->dt * p->dt, dt4 = dt2 * dt2;
+    for (int i = 0; i < hz * hz; ++i) h.c2tab[i] = c2[i];
+    for (int c = 0; c < 3; ++c) {
+      const double k1 = 2.0 * dt2 * p->weights[9 + c], k2 = 2.0 * dt4 * p->weights[3 + c];
+      for (int j = 0; j < hz; ++j)
+        for (int k = 0; k <= j; ++k) {
+          double v = 0.0;
+          for (int t = 0; t < hz; ++t) v += h.eig_u[j * hz + t] * h.eig_u[k * hz + t] / (k1 + h.eig_gamma[t] * k2);
+          h.kinv_lin[c][j * (j + 1) / 2 + k] = v;
+        }
+    }
+  }
   cudaStream_t st = (cudaStream_t)stream;
   rc = rg_check_cuda(cudaMemcpyAsync(workspace, &h, sizeof(h), cudaMemcpyHostToDevice, st), "rg_mpc_setup upload");
   if (rc != RG_OK) return rc;

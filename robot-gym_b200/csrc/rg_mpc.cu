@@ -56,25 +56,26 @@ struct Cfg {
   static constexpr int NKL = H * (H + 1) / 2;
   static constexpr int RPL = (N6 + 31) / 32;   // Psi rows per lane in the triangular sweeps
   // resident CTAs per SM the register allocation is sized for (shared memory allows 9 / 2 at h = 10 / 20)
-  static constexpr int MIN_BLOCKS = H <= 5 ? 16 : (H <= 10 ? 8 : 2);
+#ifndef RG_MIN_BLOCKS_H10
+#define RG_MIN_BLOCKS_H10 8
+#endif
+  static constexpr int MIN_BLOCKS = H <= 5 ? 16 : (H <= 10 ? RG_MIN_BLOCKS_H10 : 2);
 };
 
 template <int H>
 struct Smem {
   double psi[Cfg<H>::NPSI];        // packed lower triangle, row-major
   double kinv_ang[Cfg<H>::NKA];    // K^-1 angular block, packed, index a = 3 j + c
-  double kinv_lin[3][Cfg<H>::NKL]; // K^-1 linear channels, packed
-  double c2tab[H * H];
   double gt[H * 6];                // g~ : gradient in acceleration space
   double avec[H * 6];              // W u, right-hand sides and Woodbury solutions
   double kvec[H * 6];              // K (W u)
   double rdiag[Cfg<H>::N6];
+  double blk44[16];                // updated 4x4 diagonal block of the current Cholesky panel
   double bang[4][9];               // A_leg = I_world^-1 [r_leg]x
   double k2ang[9];
   double k1[6];
   double k2lin[3];
-  double qinv[H][9];               // (K1 + gamma_t K2)^-1 : 6 packed angular + 3 linear
-  double nblk[H][21];              // per time step: lower triangle of sum_legs B E^-1 B^T
+  double nblk[H][21];              // per time step: lower triangle of sum_legs B E^-1 B^T (setup: (K1 + gamma_t K2)^-1 scratch)
   double red[3][8];
   int flag;
 };
@@ -158,8 +159,10 @@ __device__ __noinline__ void cholesky_rows(Smem<H>& sm) {
         acc[3] = fma(-li, p3[k], acc[3]);
       }
       if (i < j0 + w) {                                // a panel row: publish the updated entries A'[i][j0..i]
+        // into the side buffer, NOT into Psi: phase 2 overwrites the panel rows of Psi with the factor
+        // while other warps may still be reading the block (that was a cross-warp race)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) if (j0 + c <= i) row_i[j0 + c] = acc[c];
+        for (int c = 0; c < 4; ++c) if (j0 + c <= i) sm.blk44[4 * (i - j0) + c] = acc[c];
       }
     }
     __syncthreads();
@@ -170,7 +173,7 @@ __device__ __noinline__ void cholesky_rows(Smem<H>& sm) {
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c <= r; ++c)
-          a[r][c] = (r < w) ? sm.psi[tri(j0 + r, j0 + c)] : (r == c ? 1.0 : 0.0);
+          a[r][c] = (r < w) ? sm.blk44[4 * r + c] : (r == c ? 1.0 : 0.0);
       // factor: l[r][c] for c < r, inverse diagonal in rd[r]
       double rd[4];
       bool bad = false;
@@ -275,7 +278,7 @@ __device__ __noinline__ void tri_solve_warp0(Smem<H>& sm) {
 
 // Row p of Psi := scale * K^-1[p][:] + (diagonal 6x6 block of sm.nblk), thread per row.
 template <int H>
-__device__ __forceinline__ void psi_build_rows(Smem<H>& sm) {
+__device__ __forceinline__ void psi_build_rows(Smem<H>& sm, const RgMpcDev* __restrict__ ws) {
   constexpr int N6 = Cfg<H>::N6;
   const int p = threadIdx.x;
   if (p < N6) {
@@ -287,7 +290,7 @@ __device__ __forceinline__ void psi_build_rows(Smem<H>& sm) {
       for (int d = 0; d <= dmax; ++d) {
         double v = 0.0;
         if (c < 3 && d < 3) v = sm.kinv_ang[tri(3 * j + c, 3 * k + d)];
-        else if (c == d) v = sm.kinv_lin[c - 3][tri(j, k)];
+        else if (c == d) v = ws->kinv_lin[c - 3][tri(j, k)];
         if (k == j) v += sm.nblk[j][c * (c + 1) / 2 + d];
         row[6 * k + d] = v;
       }
@@ -358,7 +361,7 @@ struct Blk {
 
 // out = P u for the triple held by this thread, P = 2 alpha I + W^T K W.  All threads call.
 template <int H>
-__device__ __forceinline__ void apply_p(Smem<H>& sm, const Blk& b, const double* uu, double* out) {
+__device__ __forceinline__ void apply_p(Smem<H>& sm, const RgMpcDev* __restrict__ ws, const Blk& b, const double* uu, double* out) {
   constexpr int N6 = Cfg<H>::N6;
   const int tid = threadIdx.x;
   double a6[6];
@@ -382,7 +385,7 @@ __device__ __forceinline__ void apply_p(Smem<H>& sm, const Blk& b, const double*
     if (c < 3) {
       double s20 = 0.0, s21 = 0.0, s22 = 0.0;
       for (int k = 0; k < H; ++k) {
-        const double cc = sm.c2tab[j * H + k];
+        const double cc = ws->c2tab[j * H + k];
         s20 = fma(cc, sm.avec[6 * k + 0], s20);
         s21 = fma(cc, sm.avec[6 * k + 1], s21);
         s22 = fma(cc, sm.avec[6 * k + 2], s22);
@@ -390,7 +393,7 @@ __device__ __forceinline__ void apply_p(Smem<H>& sm, const Blk& b, const double*
       val += sm.k2ang[3 * c] * s20 + sm.k2ang[3 * c + 1] * s21 + sm.k2ang[3 * c + 2] * s22;
     } else {
       double s2 = 0.0;
-      for (int k = 0; k < H; ++k) s2 = fma(sm.c2tab[j * H + k], sm.avec[6 * k + c], s2);
+      for (int k = 0; k < H; ++k) s2 = fma(ws->c2tab[j * H + k], sm.avec[6 * k + c], s2);
       val += sm.k2lin[c - 3] * s2;
     }
     sm.kvec[tid] = val;
@@ -409,7 +412,7 @@ __device__ __forceinline__ void apply_p(Smem<H>& sm, const Blk& b, const double*
 // Psi = K^-1 + sum_legs B M B^T (M = per-block symmetric 3x3, packed xx,yy,zz,xz,yz,xy), then its
 // Cholesky factor.  All threads call.
 template <int H>
-__device__ __forceinline__ void factor_psi(Smem<H>& sm, const Blk& b, const double* m) {
+__device__ __forceinline__ void factor_psi(Smem<H>& sm, const RgMpcDev* __restrict__ ws, const Blk& b, const double* m) {
   double am[9];   // A M
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
@@ -439,7 +442,7 @@ __device__ __forceinline__ void factor_psi(Smem<H>& sm, const Blk& b, const doub
     for (int i = 0; i < 21; ++i) sm.nblk[b.t][i] = n[i];
   }
   __syncthreads();
-  psi_build_rows<H>(sm);
+  psi_build_rows<H>(sm, ws);
   __syncthreads();
   cholesky_rows<H>(sm);
 }
@@ -588,8 +591,6 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 
   // ---------------------------------------------------------------- setup (thread 0..; tiny)
   if (tid == 0) sm.flag = 0;
-  // c2 table
-  for (int i = tid; i < H * H; i += blockDim.x) sm.c2tab[i] = c2f(H, i / H, i % H);
 
   // T(rpy): angular velocity -> rpy rate;  K2_ang = 2 dt^4 T^T diag(w_rpy) T
   const double tm[9] = {cy / cp, sy / cp, 0.0, -sy, cy, 0.0, cy * sp / cp, sy * sp / cp, 1.0};
@@ -669,14 +670,12 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     const double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
     const double det = m00 * c00 + m01 * c01 + m02 * c02;
     const double id = 1.0 / det;
-    sm.qinv[tid][0] = c00 * id;
-    sm.qinv[tid][1] = (m00 * m22 - m02 * m02) * id;
-    sm.qinv[tid][2] = (m00 * m11 - m01 * m01) * id;
-    sm.qinv[tid][3] = c02 * id;                       // xz
-    sm.qinv[tid][4] = (m01 * m02 - m00 * m12) * id;   // yz
-    sm.qinv[tid][5] = c01 * id;                       // xy
-#pragma unroll
-    for (int c = 0; c < 3; ++c) sm.qinv[tid][6 + c] = 1.0 / (sm.k1[3 + c] + gm * sm.k2lin[c]);
+    sm.nblk[tid][0] = c00 * id;
+    sm.nblk[tid][1] = (m00 * m22 - m02 * m02) * id;
+    sm.nblk[tid][2] = (m00 * m11 - m01 * m01) * id;
+    sm.nblk[tid][3] = c02 * id;                       // xz
+    sm.nblk[tid][4] = (m01 * m02 - m00 * m12) * id;   // yz
+    sm.nblk[tid][5] = c01 * id;                       // xy
   }
   __syncthreads();
 
@@ -692,20 +691,9 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     const int lo = c < d ? c : d, hi = c < d ? d : c;
     const int pk = (lo == hi) ? lo : (lo == 0 && hi == 2) ? 3 : (lo == 1 && hi == 2) ? 4 : 5;
     double v = 0.0;
-    for (int t = 0; t < H; ++t) v = fma(ws->eig_u[j * H + t] * ws->eig_u[k * H + t], sm.qinv[t][pk], v);
+    for (int t = 0; t < H; ++t) v = fma(ws->eig_u[j * H + t] * ws->eig_u[k * H + t], sm.nblk[t][pk], v);
     sm.kinv_ang[idx] = v;
   }
-  for (int idx = tid; idx < 3 * C::NKL; idx += blockDim.x) {
-    const int c = idx / C::NKL, r = idx % C::NKL;
-    int j = (int)((sqrt(8.0 * r + 1.0) - 1.0) * 0.5);
-    while (tri(j + 1, 0) <= r) ++j;
-    while (tri(j, 0) > r) --j;
-    const int k = r - tri(j, 0);
-    double v = 0.0;
-    for (int t = 0; t < H; ++t) v = fma(ws->eig_u[j * H + t] * ws->eig_u[k * H + t], sm.qinv[t][6 + c], v);
-    sm.kinv_lin[c][r] = v;
-  }
-
   // g~_j = 2 sum_{i>j} [ dt L_nu e_nu(i) + dt^2 (i-j-1/2) G6^T L_rho e_rho(i) ]   (thread per (j,c))
   {
     const double wx = g_rpy_rate[3 * (size_t)env + 0], wy = g_rpy_rate[3 * (size_t)env + 1], wz = g_rpy_rate[3 * (size_t)env + 2];
@@ -809,7 +797,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 #pragma unroll 1
     while (true) {
       double pu[3], rd[3], gl[3];
-      apply_p<H>(sm, blk, u, pu);
+      apply_p<H>(sm, ws, blk, u, pu);
       gt_mul(lam, mu, gl);
       double sl = 0.0, rdmax = 0.0, dmn = 0.0;
 #pragma unroll
@@ -856,7 +844,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       for (int r = 0; r < 5; ++r) inv_d[r] = 1.0 / dd[r];
       Chol5 ch;
       chol5_factor(mu, inv_d, two_alpha, ch);
-      factor_psi<H>(sm, blk, einv);
+      factor_psi<H>(sm, ws, blk, einv);
       if (sm.flag) { status |= RG_STATUS_NUMERIC; ipm_dead = true; break; }
 
       // Mehrotra predictor (phase 0: r_c = s lam, rhs = -(P u + q)) and corrector (phase 1:
@@ -1008,7 +996,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       const double inv2a = 1.0 / two_alpha;
 #pragma unroll
       for (int i = 0; i < 6; ++i) mproj[i] *= inv2a;
-      factor_psi<H>(sm, blk, mproj);
+      factor_psi<H>(sm, ws, blk, mproj);
       if (sm.flag) { status |= RG_STATUS_NUMERIC; ipm_dead = true; break; }
 
       // two passes: the solve and one step of iterative refinement
@@ -1017,7 +1005,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 #pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {
         double pu[3], ng[3], dx[3];
-        apply_p<H>(sm, blk, up, pu);
+        apply_p<H>(sm, ws, blk, up, pu);
 #pragma unroll
         for (int d = 0; d < 3; ++d) ng[d] = -(pu[d] + q[d]);
         double bprime[3];
@@ -1029,7 +1017,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 
       // --- verify: primal feasibility of the rows left out, multiplier signs of the rows held
       double pu[3], gr[3];
-      apply_p<H>(sm, blk, up, pu);
+      apply_p<H>(sm, ws, blk, up, pu);
 #pragma unroll
       for (int d = 0; d < 3; ++d) gr[d] = pu[d] + q[d];
       unsigned act_new = act;

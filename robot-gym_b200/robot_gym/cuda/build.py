@@ -30,7 +30,10 @@ NVCC_FLAGS = (
 
 
 def _extra_flags():
-    return ("-DRG_DEBUG_TRACE",) if os.environ.get("RG_DEBUG_TRACE") == "1" else ()
+    flags = ("-DRG_DEBUG_TRACE",) if os.environ.get("RG_DEBUG_TRACE") == "1" else ()
+    if os.environ.get("RG_EXTRA_NVCC_FLAGS"):          # tuning experiments, e.g. -DRG_MIN_BLOCKS_H10=7
+        flags += tuple(os.environ["RG_EXTRA_NVCC_FLAGS"].split())
+    return flags
 
 
 def _nvcc() -> str:
