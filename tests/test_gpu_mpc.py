@@ -169,7 +169,7 @@ def test_edge_cases_empty_batch_no_stance_single_leg(rg_lib, cuda_device):
 
 def test_unprepared_workspace_is_rejected(rg_lib, cuda_device):
     import ctypes
-    buf = torch.zeros(8192, dtype=torch.uint8, device=cuda_device)
+    buf = torch.zeros(32768, dtype=torch.uint8, device=cuda_device)
     x = torch.zeros((4, 12), dtype=torch.float32, device=cuda_device)
     p = ctypes.c_void_p
     rc = rg_lib.rg_mpc_build_solve(p(buf.data_ptr()), 4, p(x.data_ptr()), p(x.data_ptr()), p(x.data_ptr()),
