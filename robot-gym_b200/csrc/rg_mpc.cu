@@ -36,8 +36,13 @@ extern "C" int rg_debug_set_trace(double* dev_buf, int env) {
   return 0;
 }
 #define RG_TRACE(slot, value) do { if (g_trace && env == g_trace_env && threadIdx.x == 0) g_trace[slot] = (value); } while (0)
+// phase timers: cycles accumulated in g_trace[900 + phase] by thread 0 of the traced env
+#define RG_TIC() long long rg_t0_ = clock64()
+#define RG_TOC(phase) do { if (g_trace && (int)blockIdx.x == g_trace_env && threadIdx.x == 0) g_trace[900 + (phase)] += (double)(clock64() - rg_t0_); rg_t0_ = clock64(); } while (0)
 #else
 #define RG_TRACE(slot, value) do { } while (0)
+#define RG_TIC() do { } while (0)
+#define RG_TOC(phase) do { } while (0)
 #endif
 
 namespace {
@@ -50,7 +55,13 @@ struct Cfg {
   static constexpr int NB = 4 * H;
   static constexpr int NT = ((N6 + 31) / 32) * 32;
   static constexpr int NW = NT / 32;
-  static constexpr int NPSI = N6 * (N6 + 1) / 2;
+  // Psi rows are stored with an even number of slots each (row i holds i+1 entries) so that every row
+  // starts 16-byte aligned and the hot loops can use 128-bit shared-memory loads: see prow().
+#ifdef RG_PADDED_ROWS
+  static constexpr int NPSI = (N6 % 2 == 0) ? 2 * (N6 / 2) * (N6 / 2 + 1) : 2 * (N6 / 2 + 1) * (N6 / 2 + 1);
+#else
+  static constexpr int NPSI = N6 * (N6 + 1) / 2 + 2;   // +2: the pipelined loads may touch one pair past a short row
+#endif
   static constexpr int NA = 3 * H;
   static constexpr int NKA = NA * (NA + 1) / 2;
   static constexpr int NKL = H * (H + 1) / 2;
@@ -64,7 +75,7 @@ struct Cfg {
 
 template <int H>
 struct Smem {
-  double psi[Cfg<H>::NPSI];        // packed lower triangle, row-major
+  __align__(16) double psi[Cfg<H>::NPSI];   // lower triangle, row-major, rows padded to even length (prow)
   double kinv_ang[Cfg<H>::NKA];    // K^-1 angular block, packed, index a = 3 j + c
   double gt[H * 6];                // g~ : gradient in acceleration space
   double avec[H * 6];              // W u, right-hand sides and Woodbury solutions
@@ -81,6 +92,21 @@ struct Smem {
 };
 
 __device__ __forceinline__ int tri(int i, int k) { return i * (i + 1) / 2 + k; }
+
+// offset of row i of the lower-triangular Psi storage.
+#ifdef RG_PADDED_ROWS
+// rows padded to even length (16-byte aligned rows, 128-bit loads): sum_{r<i} 2 ceil((r+1)/2)
+__device__ __forceinline__ int prow(int i) {
+  const int p = i >> 1;
+  return (i & 1) ? 2 * (p + 1) * (p + 1) : 2 * p * (p + 1);
+}
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+#else
+// packed triangle: T(i) mod 16 is a permutation over 16 consecutive rows, so the per-column 64-bit
+// accesses of a half-warp (same column, consecutive rows) are bank-conflict free
+__device__ __forceinline__ int prow(int i) { return i * (i + 1) / 2; }
+__device__ __forceinline__ double2 ld2(const double* p) { return make_double2(p[0], p[1]); }
+#endif
 
 __device__ __forceinline__ double c1f(int h, int j, int k) { return (double)(h - (j > k ? j : k)); }
 
@@ -136,7 +162,7 @@ __device__ __noinline__ void cholesky_rows(Smem<H>& sm) {
   constexpr int N6 = Cfg<H>::N6;
   const int i = threadIdx.x;
   const bool row_ok = i < N6;
-  double* row_i = sm.psi + tri(row_ok ? i : 0, 0);
+  double* row_i = sm.psi + prow(row_ok ? i : 0);
   if (i == 0) sm.flag = 0;   // published by the first barrier below
 #pragma unroll 1
   for (int j0 = 0; j0 < N6; j0 += 4) {
@@ -144,19 +170,26 @@ __device__ __noinline__ void cholesky_rows(Smem<H>& sm) {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     const bool in_play = row_ok && i >= j0;
     if (in_play) {
-      const double* p0 = sm.psi + tri(j0, 0);
-      const double* p1 = sm.psi + tri(j0 + (w > 1 ? 1 : 0), 0);
-      const double* p2 = sm.psi + tri(j0 + (w > 2 ? 2 : 0), 0);
-      const double* p3 = sm.psi + tri(j0 + (w > 3 ? 3 : 0), 0);
+      const double* r2 = row_i;
+      const double* p0 = sm.psi + prow(j0);
+      const double* p1 = sm.psi + prow(j0 + (w > 1 ? 1 : 0));
+      const double* p2 = sm.psi + prow(j0 + (w > 2 ? 2 : 0));
+      const double* p3 = sm.psi + prow(j0 + (w > 3 ? 3 : 0));
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[c] = (c < w && j0 + c <= i) ? row_i[j0 + c] : 0.0;
+      // software-pipelined dot products: the 128-bit loads of step g+1 are in flight while step g's
+      // eight FMAs retire (the loop is latency-bound on shared memory otherwise: 2 warps per CTA)
+      const int ng = j0 >> 1;                          // pairs of columns already factored (j0 % 4 == 0)
+      double2 a = ld2(r2), b0 = ld2(p0), b1 = ld2(p1), b2 = ld2(p2), b3 = ld2(p3);
 #pragma unroll 2
-      for (int k = 0; k < j0; ++k) {
-        const double li = row_i[k];
-        acc[0] = fma(-li, p0[k], acc[0]);
-        acc[1] = fma(-li, p1[k], acc[1]);
-        acc[2] = fma(-li, p2[k], acc[2]);
-        acc[3] = fma(-li, p3[k], acc[3]);
+      for (int g = 0; g < ng; ++g) {
+        const int gn = g + 1 < ng ? g + 1 : g;
+        const double2 an = ld2(r2 + 2 * gn), c0 = ld2(p0 + 2 * gn), c1 = ld2(p1 + 2 * gn), c2 = ld2(p2 + 2 * gn), c3 = ld2(p3 + 2 * gn);
+        acc[0] = fma(-a.x, b0.x, acc[0]); acc[1] = fma(-a.x, b1.x, acc[1]);
+        acc[2] = fma(-a.x, b2.x, acc[2]); acc[3] = fma(-a.x, b3.x, acc[3]);
+        acc[0] = fma(-a.y, b0.y, acc[0]); acc[1] = fma(-a.y, b1.y, acc[1]);
+        acc[2] = fma(-a.y, b2.y, acc[2]); acc[3] = fma(-a.y, b3.y, acc[3]);
+        a = an; b0 = c0; b1 = c1; b2 = c2; b3 = c3;
       }
       if (i < j0 + w) {                                // a panel row: publish the updated entries A'[i][j0..i]
         // into the side buffer, NOT into Psi: phase 2 overwrites the panel rows of Psi with the factor
@@ -235,7 +268,7 @@ __device__ __noinline__ void tri_solve_warp0(Smem<H>& sm) {
   for (int r = 0; r < RPL; ++r) {
     const int i = lane + 32 * r;
     x[r] = i < N6 ? sm.avec[i] : 0.0;
-    base[r] = tri(i < N6 ? i : 0, 0);
+    base[r] = prow(i < N6 ? i : 0);
   }
   // forward: L y = b
 #pragma unroll
@@ -264,7 +297,7 @@ __device__ __noinline__ void tri_solve_warp0(Smem<H>& sm) {
       double xj = x[slot] * sm.rdiag[j];
       xj = __shfl_sync(kFull, xj, jj);
       if (lane == jj) x[slot] = xj;
-      const double* row_j = sm.psi + tri(j, 0);
+      const double* row_j = sm.psi + prow(j);
 #pragma unroll
       for (int r = 0; r <= slot; ++r) {
         const int i = lane + 32 * r;
@@ -283,17 +316,34 @@ __device__ __forceinline__ void psi_build_rows(Smem<H>& sm, const RgMpcDev* __re
   const int p = threadIdx.x;
   if (p < N6) {
     const int j = p / 6, c = p - 6 * j;
-    double* row = sm.psi + tri(p, 0);
-#pragma unroll 1
-    for (int k = 0; k <= j; ++k) {
-      const int dmax = k == j ? c : 5;
-      for (int d = 0; d <= dmax; ++d) {
-        double v = 0.0;
-        if (c < 3 && d < 3) v = sm.kinv_ang[tri(3 * j + c, 3 * k + d)];
-        else if (c == d) v = ws->kinv_lin[c - 3][tri(j, k)];
-        if (k == j) v += sm.nblk[j][c * (c + 1) / 2 + d];
-        row[6 * k + d] = v;
+    double* row = sm.psi + prow(p);
+    // K^-1 couples channel c with the three angular channels (c < 3) or only with itself (c >= 3)
+    if (c < 3) {
+      const double* ka = sm.kinv_ang + tri(3 * j + c, 0);
+#pragma unroll 2
+      for (int k = 0; k < j; ++k) {
+        double* dst = row + 6 * k;
+        const double v0 = ka[3 * k], v1 = ka[3 * k + 1], v2 = ka[3 * k + 2];
+        dst[0] = v0; dst[1] = v1; dst[2] = v2; dst[3] = 0.0; dst[4] = 0.0; dst[5] = 0.0;
       }
+    } else {
+      const double* kl = ws->kinv_lin[c - 3] + tri(j, 0);
+#pragma unroll 2
+      for (int k = 0; k < j; ++k) {
+        double* dst = row + 6 * k;
+        const double v = kl[k];
+        dst[0] = 0.0; dst[1] = 0.0; dst[2] = 0.0;
+        dst[3] = c == 3 ? v : 0.0; dst[4] = c == 4 ? v : 0.0; dst[5] = c == 5 ? v : 0.0;
+      }
+    }
+    // diagonal time block: columns d <= c, plus this step's sum_legs B E^-1 B^T
+    const double* nb = sm.nblk[j] + c * (c + 1) / 2;
+    double* dst = row + 6 * j;
+    for (int d = 0; d <= c; ++d) {
+      double v = nb[d];
+      if (c < 3) v += sm.kinv_ang[tri(3 * j + c, 3 * j + d)];
+      else if (d == c) v += ws->kinv_lin[c - 3][tri(j, j)];
+      dst[d] = v;
     }
   }
 }
@@ -442,9 +492,12 @@ __device__ __forceinline__ void factor_psi(Smem<H>& sm, const RgMpcDev* __restri
     for (int i = 0; i < 21; ++i) sm.nblk[b.t][i] = n[i];
   }
   __syncthreads();
+  RG_TIC();
   psi_build_rows<H>(sm, ws);
   __syncthreads();
+  RG_TOC(10);
   cholesky_rows<H>(sm);
+  RG_TOC(11);
 }
 
 // First half of x = (E + W^T K W)^-1 rhs through the Woodbury identity: given the per-block E^-1
@@ -728,6 +781,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   }
   __syncthreads();
 
+  RG_TIC();
   // ---------------------------------------------------------------- per-block constants
   Blk blk;
 #pragma unroll
@@ -797,7 +851,9 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 #pragma unroll 1
     while (true) {
       double pu[3], rd[3], gl[3];
+      RG_TOC(0);
       apply_p<H>(sm, ws, blk, u, pu);
+      RG_TOC(1);
       gt_mul(lam, mu, gl);
       double sl = 0.0, rdmax = 0.0, dmn = 0.0;
 #pragma unroll
@@ -844,7 +900,9 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       for (int r = 0; r < 5; ++r) inv_d[r] = 1.0 / dd[r];
       Chol5 ch;
       chol5_factor(mu, inv_d, two_alpha, ch);
+      RG_TOC(2);
       factor_psi<H>(sm, ws, blk, einv);
+      RG_TOC(3);
       if (sm.flag) { status |= RG_STATUS_NUMERIC; ipm_dead = true; break; }
 
       // Mehrotra predictor (phase 0: r_c = s lam, rhs = -(P u + q)) and corrector (phase 1:
@@ -866,7 +924,9 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
           for (int d = 0; d < 3; ++d) rhs[d] = -rd[d] + gw[d];
         }
         double bprime[3];
+        RG_TOC(4);
         woodbury_solve<H>(sm, blk, einv, rhs, bprime);
+        RG_TOC(5);
         chol5_block_solve(ch, mu, inv_d, two_alpha, bprime, dx, c5);   // c5 = G dx without cancellation
         if (phase == 0) {
           // x_r = ds_r / s_r ; dl_r / lam_r = -1 - x_r: the largest feasible affine step is 1 / max(-x, 1 + x)
@@ -927,6 +987,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       continue;
     }
 
+    RG_TOC(6);
     // -------------------------------------------------------------- active-set polish
     unsigned act = 0;
 #pragma unroll
@@ -1045,7 +1106,12 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
           if (ysgn < -1e-10 * qscale) act_new &= ~(1u << rows[i]);
         }
       }
-      double changed = (act_new != act) ? 1.0 : 0.0, dmx = 0.0, dmn = 0.0;
+      // stationarity on the free subspace is what the solve is supposed to deliver; check it anyway so
+      // that a wrong factorisation can never be reported as a verified optimum:  |Z Z^T (P u + q)|_inf
+      double pg[3];
+      sym3_mul(mproj, gr, pg);
+      const double pgmax = active_blk ? two_alpha * fmax(fabs(pg[0]), fmax(fabs(pg[1]), fabs(pg[2]))) : 0.0;
+      double changed = (act_new != act || pgmax > 1e-7 * qscale) ? 1.0 : 0.0, dmx = 0.0, dmn = 0.0;
       block_reduce<C::NW>(changed, dmx, dmn, sm.red);
       act = act_new;
 #ifdef RG_DEBUG_TRACE
@@ -1076,6 +1142,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     for (int d = 0; d < 3; ++d) u_out[d] = u_best[d];
   }
 
+  RG_TOC(7);
   // ---------------------------------------------------------------- outputs (negated solution)
   if (is_blk) {
     const float fx = active_blk ? (float)(-u_out[0]) : 0.f;
@@ -1108,8 +1175,16 @@ int launch_h(const RgMpcDev* ws, int n_env, const float* com_vel, const float* r
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(mpc_solve_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return rg_check_cuda(e, "cudaFuncSetAttribute(mpc_solve_kernel)");
-    // the default carveout leaves room for only ~5 CTAs of 24 KB: ask for the full 227 KB of shared memory
-    e = cudaFuncSetAttribute(mpc_solve_kernel<H>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // the default carveout leaves room for only ~5 CTAs: ask for what MIN_BLOCKS resident CTAs need and no
+    // more, so that the rest of the 228 KB stays L1 (register spills and the parameter block live there)
+#ifndef RG_CARVEOUT_PCT
+    const int need_kb = (int)((Cfg<H>::MIN_BLOCKS * (smem + 1024) + 1023) / 1024);
+    int carveout = (need_kb * 100 + 227) / 228 + 1;
+    if (carveout > 100) carveout = 100;
+#else
+    const int carveout = RG_CARVEOUT_PCT;
+#endif
+    e = cudaFuncSetAttribute(mpc_solve_kernel<H>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
     if (e != cudaSuccess) return rg_check_cuda(e, "cudaFuncSetAttribute(carveout)");
     attr_set = true;
   }
@@ -1119,7 +1194,51 @@ int launch_h(const RgMpcDev* ws, int n_env, const float* com_vel, const float* r
   return rg_check_cuda(cudaGetLastError(), "mpc_solve_kernel launch");
 }
 
+
+// ---- debug / self-test hook (not part of the public header): factor a dense SPD matrix given in
+// row-major N6 x N6 and solve one right-hand side with the kernel's own Cholesky / sweep routines.
+template <int H>
+__global__ void __launch_bounds__(Cfg<H>::NT) chol_selftest_kernel(const double* __restrict__ a_dense,
+                                                                   const double* __restrict__ rhs, double* __restrict__ x_out,
+                                                                   double* __restrict__ l_out) {
+  constexpr int N6 = Cfg<H>::N6;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<H>& sm = *reinterpret_cast<Smem<H>*>(smem_raw);
+  const int tid = threadIdx.x;
+  if (tid < N6) {
+    for (int k = 0; k <= tid; ++k) sm.psi[prow(tid) + k] = a_dense[tid * N6 + k];
+    sm.avec[tid] = rhs[tid];
+  }
+  __syncthreads();
+  cholesky_rows<H>(sm);
+  if (tid < 32) tri_solve_warp0<H>(sm);
+  __syncthreads();
+  if (tid < N6) {
+    x_out[tid] = sm.avec[tid];
+    for (int k = 0; k < tid; ++k) l_out[tid * N6 + k] = sm.psi[prow(tid) + k];
+    l_out[tid * N6 + tid] = 1.0 / sm.rdiag[tid];
+  }
+}
+
+template <int H>
+int chol_selftest_launch(const double* a, const double* b, double* x, double* l, cudaStream_t st) {
+  const size_t smem = sizeof(Smem<H>);
+  cudaError_t e = cudaFuncSetAttribute(chol_selftest_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return rg_check_cuda(e, "cudaFuncSetAttribute(chol_selftest_kernel)");
+  chol_selftest_kernel<H><<<1, Cfg<H>::NT, smem, st>>>(a, b, x, l);
+  return rg_check_cuda(cudaGetLastError(), "chol_selftest_kernel launch");
+}
+
 }  // namespace
+
+extern "C" int rg_debug_chol_solve(int horizon, const double* a_dense, const double* rhs, double* x_out, double* l_out, void* stream) {
+  switch (horizon) {
+    case 5: return chol_selftest_launch<5>(a_dense, rhs, x_out, l_out, (cudaStream_t)stream);
+    case 10: return chol_selftest_launch<10>(a_dense, rhs, x_out, l_out, (cudaStream_t)stream);
+    case 20: return chol_selftest_launch<20>(a_dense, rhs, x_out, l_out, (cudaStream_t)stream);
+    default: rg_set_error("unsupported horizon %d", horizon); return RG_ERR_UNSUPPORTED;
+  }
+}
 
 int rg_launch_mpc(const RgMpcDev* ws, int horizon, int n_env, const float* com_vel, const float* rpy,
                   const float* rpy_rate, const uint8_t* contacts, const float* feet, const float* command,
