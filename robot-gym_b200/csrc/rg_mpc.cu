@@ -60,7 +60,7 @@ struct Cfg {
 #ifdef RG_PADDED_ROWS
   static constexpr int NPSI = (N6 % 2 == 0) ? 2 * (N6 / 2) * (N6 / 2 + 1) : 2 * (N6 / 2 + 1) * (N6 / 2 + 1);
 #else
-  static constexpr int NPSI = N6 * (N6 + 1) / 2 + 2;   // +2: the pipelined loads may touch one pair past a short row
+  static constexpr int NPSI = N6 * (N6 + 1) / 2 + 64;   // slack: the pipelined loads of the factor routines over-read (values unused)
 #endif
   static constexpr int NA = 3 * H;
   static constexpr int NKA = NA * (NA + 1) / 2;
@@ -257,6 +257,8 @@ __device__ __noinline__ void cholesky_rows(Smem<H>& sm) {
 
 // ---- Psi x = b with the factor, b/x in sm.avec; executed by warp 0 only ----------------------
 // Each lane owns rows lane, lane+32, ...; the pivot value travels by __shfl, no block barrier.
+// (Tried and measured slower under load: 4x4-blocked sweeps with precomputed block inverses, and
+// register prefetch of the next column -- other resident warps already hide the shared-memory latency.)
 template <int H>
 __device__ __noinline__ void tri_solve_warp0(Smem<H>& sm) {
   constexpr int N6 = Cfg<H>::N6;
