@@ -861,14 +861,13 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 #pragma unroll
       for (int d = 0; d < 3; ++d) { rd[d] = pu[d] + q[d] + gl[d]; rdmax = fmax(rdmax, fabs(rd[d])); }
       // sl_r = s lam and its reciprocal: the only ten divisions of the iteration
-      double slr[10], is[10], il[10];
+      // only isl stays live across the factorisation and the solves: 1/s = lam isl, 1/lam = s isl
+      double isl[10];
 #pragma unroll
       for (int r = 0; r < 10; ++r) {
-        slr[r] = s[r] * lam[r];
-        const double isl = 1.0 / slr[r];
-        is[r] = lam[r] * isl;     // 1 / s
-        il[r] = s[r] * isl;       // 1 / lam
-        sl += slr[r];
+        const double slr = s[r] * lam[r];
+        isl[r] = 1.0 / slr;
+        sl += slr;
       }
       if (!active_blk) { sl = 0.0; rdmax = 0.0; }
       block_reduce<C::NW>(sl, rdmax, dmn, sm.red);
@@ -895,7 +894,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       // block 3x3 parts and Psi
       double dd[5], einv[6];
 #pragma unroll
-      for (int r = 0; r < 5; ++r) dd[r] = lam[r] * is[r] + lam[5 + r] * is[5 + r];
+      for (int r = 0; r < 5; ++r) dd[r] = lam[r] * lam[r] * isl[r] + lam[5 + r] * lam[5 + r] * isl[5 + r];
       block_inverse(dd, mu, two_alpha, einv);
       double inv_d[5];
 #pragma unroll
@@ -936,7 +935,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
           double xr[10];
 #pragma unroll
           for (int r = 0; r < 10; ++r) {
-            xr[r] = (r < 5 ? -c5[r] : c5[r - 5]) * is[r];
+            xr[r] = (r < 5 ? -c5[r] : c5[r - 5]) * (lam[r] * isl[r]);
             if (active_blk) tmax = fmax(tmax, fmax(-xr[r], 1.0 + xr[r]));
           }
           block_reduce<C::NW>(dsum, tmax, dmn2, sm.red);
@@ -944,8 +943,9 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
           double mu_aff = 0.0;
 #pragma unroll
           for (int r = 0; r < 10; ++r) {
-            mu_aff += slr[r] * (1.0 + amax * xr[r]) * (1.0 - amax * (1.0 + xr[r]));
-            wv[r] = -slr[r] * xr[r] * (1.0 + xr[r]);          // ds_a dl_a
+            const double slr = s[r] * lam[r];
+            mu_aff += slr * (1.0 + amax * xr[r]) * (1.0 - amax * (1.0 + xr[r]));
+            wv[r] = -slr * xr[r] * (1.0 + xr[r]);             // ds_a dl_a
           }
           if (!active_blk) mu_aff = 0.0;
           double dmx3 = 0.0, dmn3 = 0.0;
@@ -954,7 +954,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
           const double ratio = mu_aff / mu_c;
           sigmu = ratio * ratio * ratio * mu_c;
 #pragma unroll
-          for (int r = 0; r < 10; ++r) wv[r] = (slr[r] + wv[r] - sigmu) * is[r];   // r_c / s
+          for (int r = 0; r < 10; ++r) wv[r] = (s[r] * lam[r] + wv[r] - sigmu) * (lam[r] * isl[r]);   // r_c / s
         }
       }
       // step to the boundary: -ds/s = -y, -dl/lam = w/lam + y with y = ds/s
@@ -962,8 +962,8 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       double yr[10];
 #pragma unroll
       for (int r = 0; r < 10; ++r) {
-        yr[r] = (r < 5 ? -c5[r] : c5[r - 5]) * is[r];
-        if (active_blk) tmax = fmax(tmax, fmax(-yr[r], wv[r] * il[r] + yr[r]));
+        yr[r] = (r < 5 ? -c5[r] : c5[r - 5]) * (lam[r] * isl[r]);
+        if (active_blk) tmax = fmax(tmax, fmax(-yr[r], wv[r] * (s[r] * isl[r]) + yr[r]));
       }
       block_reduce<C::NW>(dsum, tmax, dmn2, sm.red);
       // fraction to the boundary: 0.99 far out, 0.999 once both residuals are small (a step closer to 1
