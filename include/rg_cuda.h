@@ -59,7 +59,8 @@ enum {
   RG_STATUS_POLISHED = 1,        /* active-set polish verified (exact KKT point of the QP) */
   RG_STATUS_IPM_CONVERGED = 2,   /* interior-point residual below tolerance */
   RG_STATUS_NO_STANCE = 4,       /* no foot in contact: all forces are zero by the bounds */
-  RG_STATUS_NUMERIC = 8          /* non-positive pivot met (result is the last good iterate) */
+  RG_STATUS_NUMERIC = 8,         /* non-positive pivot met (result is the last good iterate) */
+  RG_STATUS_ACTIVE_SET_ONLY = 16 /* the cold-start active-set iteration verified; no interior point ran */
 };
 
 /* ---- ConvexMpc constructor arguments + the constants compiled into mpc_osqp ------------
@@ -84,6 +85,10 @@ typedef struct rg_mpc_params {
   double ipm_tol;              /* relative residual at which the interior point hands over (1e-6) */
   int32_t max_ipm_iters;       /* hard cap (40) */
   int32_t max_polish_rounds;   /* 0 disables the active-set polish; rounds per attempt (3) */
+  int32_t cold_start_rounds;   /* active-set rounds tried from the unconstrained minimiser BEFORE the
+                                  interior point (4); 0 = always run the interior point first */
+  int32_t cold_start_max_violations; /* give the cold start up when the unconstrained minimiser violates
+                                  more rows than this (16 * horizon / 10) */
 } rg_mpc_params;
 
 /* Fill `p` with the motion_imitation defaults for the given mass/inertia/height. */

@@ -13,6 +13,8 @@ struct RgMpcDev {
   int32_t horizon;
   int32_t max_ipm_iters;
   int32_t max_polish_rounds;
+  int32_t cold_start_rounds;
+  int32_t cold_start_max_violations;
   double inv_mass;
   double inv_inertia[9];   // body frame
   double dt;

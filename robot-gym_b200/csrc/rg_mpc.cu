@@ -120,6 +120,13 @@ __device__ __forceinline__ double c2f(int h, int j, int k) {
   return s2 - (a + b) * s1 + a * b * cnt;
 }
 
+// After the first solve of an active-set round the refinement pass is skipped when the projected
+// gradient is already below this (relative to the gradient scale): the error it leaves in the
+// weakly curved directions is <= tol / (2 alpha).
+#ifndef RG_SKIP_REFINE_TOL
+#define RG_SKIP_REFINE_TOL 1e-11
+#endif
+
 // ---- block-wide reductions (all threads call; result valid in all threads) -------------------
 template <int NW>
 __device__ __forceinline__ void block_reduce(double& sum, double& mx, double& mn, double (*red)[8]) {
@@ -847,9 +854,17 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   double u_best[3] = {u[0], u[1], u[2]};
   int stall = 0;
   bool done = false;
+  // Attempt -1 is the cold start: the same active-set iteration started from the empty set (round 0
+  // is the unconstrained minimiser), with no interior point before it.  Most trot-like problems have
+  // a handful of active rows and verify within 2-3 rounds; the ones that do not fall
+  // through to the interior point untouched.
+  const int cold_rounds = ws->cold_start_rounds;
+  const double cold_max_viol = (double)ws->cold_start_max_violations;
 #pragma unroll 1
-  for (int attempt = 0; attempt < 3 && !done; ++attempt) {
+  for (int attempt = cold_rounds > 0 ? -1 : 0; attempt < 3 && !done; ++attempt) {
     bool converged = false, ipm_dead = false;
+    const bool cold = attempt < 0;
+    if (!cold) {
 #pragma unroll 1
     while (true) {
       double pu[3], rd[3], gl[3];
@@ -988,16 +1003,19 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       tol = 1e-9;        // without the polish the interior point itself has to resolve the alpha-directions
       continue;
     }
+    }   // !cold
 
     RG_TOC(6);
     // -------------------------------------------------------------- active-set polish
     unsigned act = 0;
+    if (!cold) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) if (active_blk && lam[r] > 0.03 * s[r]) act |= 1u << r;
+      for (int r = 0; r < 10; ++r) if (active_blk && lam[r] > 0.03 * s[r]) act |= 1u << r;
+    }
     bool polished = false;
     double up[3] = {0.0, 0.0, 0.0};
     // 3, 6, 12 rounds: later attempts start from a sharper guess; a dead interior point gets the full budget
-    const int round_budget = ipm_dead ? (max_polish << 2) : (max_polish << attempt);
+    const int round_budget = cold ? cold_rounds : ipm_dead ? (max_polish << 2) : (max_polish << attempt);
 #pragma unroll 1
     for (int round = 0; round < round_budget; ++round) {
       ++polish_rounds;
@@ -1060,74 +1078,95 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 #pragma unroll
       for (int i = 0; i < 6; ++i) mproj[i] *= inv2a;
       factor_psi<H>(sm, ws, blk, mproj);
-      if (sm.flag) { status |= RG_STATUS_NUMERIC; ipm_dead = true; break; }
+      if (sm.flag) {
+        if (!cold) { status |= RG_STATUS_NUMERIC; ipm_dead = true; }   // a failed cold start just hands over
+        break;
+      }
 
-      // two passes: the solve and one step of iterative refinement
+      // gr = P u + q at the particular solution (u0 = 0 in the first cold round)
 #pragma unroll
       for (int d = 0; d < 3; ++d) up[d] = u0[d];
-#pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        double pu[3], ng[3], dx[3];
+      double gr[3];
+      if (cold && round == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) gr[d] = q[d];
+      } else {
+        double pu[3];
         apply_p<H>(sm, ws, blk, up, pu);
 #pragma unroll
-        for (int d = 0; d < 3; ++d) ng[d] = -(pu[d] + q[d]);
-        double bprime[3];
+        for (int d = 0; d < 3; ++d) gr[d] = pu[d] + q[d];
+      }
+      // Pass 0 is the solve, pass 1 one step of iterative refinement.  The active set is checked after
+      // each: when it moves after pass 0 the refinement would be wasted (the next round starts over),
+      // and it is skipped as well when pass 0 already left a projected gradient at rounding level.
+      unsigned act_new = act;
+      double nchg = 0.0, pgm = 0.0;
+      bool accept = false;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        double ng[3], bprime[3], dx[3], pu[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) ng[d] = -gr[d];
         woodbury_solve<H>(sm, blk, mproj, ng, bprime);
         sym3_mul(mproj, bprime, dx);
 #pragma unroll
         for (int d = 0; d < 3; ++d) up[d] += dx[d];
-      }
+        apply_p<H>(sm, ws, blk, up, pu);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) gr[d] = pu[d] + q[d];
 
-      // --- verify: primal feasibility of the rows left out, multiplier signs of the rows held
-      double pu[3], gr[3];
-      apply_p<H>(sm, ws, blk, up, pu);
+        // --- verify: primal feasibility of the rows left out, multiplier signs of the rows held
+        act_new = act;
+        if (active_blk) {
+          double c5[5];
+          g_mul(up, mu, c5);
+          const double ftol = 1e-9 * fzmax;
 #pragma unroll
-      for (int d = 0; d < 3; ++d) gr[d] = pu[d] + q[d];
-      unsigned act_new = act;
-      if (active_blk) {
-        double c5[5];
-        g_mul(up, mu, c5);
-        const double ftol = 1e-9 * fzmax;
-#pragma unroll
-        for (int r = 0; r < 10; ++r) {
-          const double slack = r < 5 ? hv_up[r] - c5[r] : c5[r - 5] - lo_b[r - 5];
-          if (!((act >> r) & 1u) && slack < -ftol) act_new |= 1u << r;
-        }
-        // multipliers: sum_i y_i a_i = -gr on span(e)
-        double y[3] = {0, 0, 0};
+          for (int r = 0; r < 10; ++r) {
+            const double slack = r < 5 ? hv_up[r] - c5[r] : c5[r - 5] - lo_b[r - 5];
+            if (!((act >> r) & 1u) && slack < -ftol) act_new |= 1u << r;
+          }
+          // multipliers: sum_i y_i a_i = -gr on span(e)
+          double y[3] = {0, 0, 0};
 #pragma unroll 1
-        for (int i = na - 1; i >= 0; --i) {
-          double v = -(gr[0] * e[i][0] + gr[1] * e[i][1] + gr[2] * e[i][2]);
-          for (int k = i + 1; k < na; ++k) v -= rr[i][k] * y[k];
-          y[i] = v / rr[i][i];
-        }
+          for (int i = na - 1; i >= 0; --i) {
+            double v = -(gr[0] * e[i][0] + gr[1] * e[i][1] + gr[2] * e[i][2]);
+            for (int k = i + 1; k < na; ++k) v -= rr[i][k] * y[k];
+            y[i] = v / rr[i][i];
+          }
 #pragma unroll 1
-        for (int i = 0; i < na; ++i) {
-          // upper-bound rows need y >= 0, lower-bound rows y <= 0
-          const double ysgn = rows[i] < 5 ? y[i] : -y[i];
-          if (ysgn < -1e-10 * qscale) act_new &= ~(1u << rows[i]);
+          for (int i = 0; i < na; ++i) {
+            // upper-bound rows need y >= 0, lower-bound rows y <= 0
+            const double ysgn = rows[i] < 5 ? y[i] : -y[i];
+            if (ysgn < -1e-10 * qscale) act_new &= ~(1u << rows[i]);
+          }
         }
+        // stationarity on the free subspace is what the solve is supposed to deliver; check it anyway so
+        // that a wrong factorisation can never be reported as a verified optimum:  |Z Z^T (P u + q)|_inf
+        double pg[3];
+        sym3_mul(mproj, gr, pg);
+        pgm = active_blk ? two_alpha * fmax(fabs(pg[0]), fmax(fabs(pg[1]), fabs(pg[2]))) : 0.0;
+        nchg = (double)__popc(act_new ^ act);
+        double dmn = 0.0;
+        block_reduce<C::NW>(nchg, pgm, dmn, sm.red);
+        if (nchg > 0.0) break;
+        if (pgm <= (pass == 0 ? RG_SKIP_REFINE_TOL : 1e-7) * qscale) { accept = true; break; }
       }
-      // stationarity on the free subspace is what the solve is supposed to deliver; check it anyway so
-      // that a wrong factorisation can never be reported as a verified optimum:  |Z Z^T (P u + q)|_inf
-      double pg[3];
-      sym3_mul(mproj, gr, pg);
-      const double pgmax = active_blk ? two_alpha * fmax(fabs(pg[0]), fmax(fabs(pg[1]), fabs(pg[2]))) : 0.0;
-      double changed = (act_new != act || pgmax > 1e-7 * qscale) ? 1.0 : 0.0, dmx = 0.0, dmn = 0.0;
-      block_reduce<C::NW>(changed, dmx, dmn, sm.red);
-      act = act_new;
 #ifdef RG_DEBUG_TRACE
       {
-        double cnt = (double)__popc(act), dmx2 = 0.0, dmn2 = 0.0;
+        double cnt = (double)__popc(act_new), dmx2 = 0.0, dmn2 = 0.0;
         block_reduce<C::NW>(cnt, dmx2, dmn2, sm.red);
-        RG_TRACE(4 * trace_n + 0, -1.0); RG_TRACE(4 * trace_n + 1, changed); RG_TRACE(4 * trace_n + 2, cnt); RG_TRACE(4 * trace_n + 3, (double)round);
+        RG_TRACE(4 * trace_n + 0, cold ? -2.0 : -1.0); RG_TRACE(4 * trace_n + 1, nchg); RG_TRACE(4 * trace_n + 2, cnt); RG_TRACE(4 * trace_n + 3, pgm / qscale);
         ++trace_n;
       }
 #endif
-      if (changed == 0.0) { polished = true; break; }
+      if (accept) { polished = true; break; }
+      // too many rows violated by the unconstrained minimiser: the interior point is the better tool
+      if (cold && round == 0 && nchg > cold_max_viol) break;
+      act = act_new;
     }
     if (polished) {
-      status |= RG_STATUS_POLISHED;
+      status |= cold ? (RG_STATUS_POLISHED | RG_STATUS_ACTIVE_SET_ONLY) : RG_STATUS_POLISHED;
 #pragma unroll
       for (int d = 0; d < 3; ++d) u_out[d] = up[d];
       double cnt = (double)__popc(act), dmx = 0.0, dmn = 0.0;
@@ -1137,6 +1176,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       break;
     }
     if (ipm_dead) break;
+    if (cold) continue;
     tol = fmax(tol * 1e-2, 1e-9);   // float64 interior-point iterates are trustworthy down to ~1e-9 here
   }
   if (!done) {

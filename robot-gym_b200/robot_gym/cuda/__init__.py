@@ -21,6 +21,7 @@ RG_VEL_WINDOW_MAX = 64
 RG_LEG_SWING, RG_LEG_STANCE, RG_LEG_EARLY_CONTACT, RG_LEG_LOSE_CONTACT = 0, 1, 2, 3
 RG_INFO_IPM_ITERS, RG_INFO_POLISH_ROUNDS, RG_INFO_STATUS, RG_INFO_NUM_ACTIVE = 0, 1, 2, 3
 RG_STATUS_POLISHED, RG_STATUS_IPM_CONVERGED, RG_STATUS_NO_STANCE, RG_STATUS_NUMERIC = 1, 2, 4, 8
+RG_STATUS_ACTIVE_SET_ONLY = 16
 
 # every symbol include/rg_cuda.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
@@ -40,6 +41,7 @@ class MpcParams(Structure):
         ("friction_coeffs", c_double * 4), ("gravity", c_double), ("fz_max", c_double),
         ("fz_min", c_double), ("desired_body_height", c_double), ("ipm_tol", c_double),
         ("max_ipm_iters", c_int32), ("max_polish_rounds", c_int32),
+        ("cold_start_rounds", c_int32), ("cold_start_max_violations", c_int32),
     ]
 
 

@@ -168,4 +168,6 @@ def test_controller_batched_subset_reset_and_stats(rg_lib, cuda_device):
     ctl.reset(ids)
     assert ctl.reset_time[3].item() == 0.2 and ctl.reset_time[4].item() == 0.0
     stats = ctl.rollout_stats().cpu().numpy()
-    assert stats[0] == 256 and stats[4] == 256 and stats[6] == 0 and 3 <= stats[1] / 256 <= 12
+    assert stats[0] == 256 and stats[4] == 256 and stats[6] == 0
+    # most solves verify from the cold-start active-set iteration (0 interior-point iterations)
+    assert 0 <= stats[1] / 256 <= 12 and 1 <= stats[3] / 256 <= 12

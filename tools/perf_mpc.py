@@ -37,7 +37,7 @@ def main():
                 ref, _, _ = c_oracle.solve_batch(convex_mpc.MpcParams(horizon=horizon), st.slice(0, m), ctrl.MPC_BODY_HEIGHT, n_threads=os.cpu_count())
                 err = (np.abs(fo[:m] - ref).max(axis=1) / np.maximum(1, np.abs(ref).max(axis=1))).max()
                 print(f"h={horizon} n={n} all_stance={all_stance}: {med:.3f} ms  {n/med*1e3:,.0f} solves/s | iters {inf[:,0].mean():.2f} polish {inf[:,1].mean():.2f} "
-                      f"polished {np.mean((inf[:,2]&1)!=0):.4f} | worst rel err vs C oracle {err:.2e}")
+                      f"polished {np.mean((inf[:,2]&1)!=0):.4f} cold {np.mean((inf[:,2]&16)!=0):.3f} | worst rel err vs C oracle {err:.2e}")
 
 if __name__ == "__main__":
     main()
