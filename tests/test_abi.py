@@ -39,7 +39,7 @@ def test_library_is_built_for_sm_100a_only(rg_lib):
 
 def test_struct_layouts_match_header_sizes(rg_lib):
     # sizes computed from the header's field lists (8-byte aligned doubles, 4-byte ints)
-    assert ctypes.sizeof(rg.MpcParams) == 8 + 72 + 4 + 4 + 8 + 104 + 8 + 32 + 8 + 8 + 8 + 8 + 8 + 4 + 4
+    assert ctypes.sizeof(rg.MpcParams) == 8 + 72 + 4 + 4 + 8 + 104 + 8 + 32 + 8 + 8 + 8 + 8 + 8 + 4 + 4 + 4 + 4
     assert ctypes.sizeof(rg.LegChain) == 8 * (9 + 27 + 9 + 3 + 2)
     assert ctypes.sizeof(rg.ControllerState) == 8 * 28
 
@@ -51,6 +51,7 @@ def test_default_params_follow_motion_imitation_defaults(rg_lib):
     assert list(p.friction_coeffs) == [0.45] * 4
     assert p.fz_max == pytest.approx(1900.0) and p.fz_min == pytest.approx(19.0)
     assert p.desired_body_height == 0.42
+    assert p.cold_start_rounds == 4 and p.cold_start_max_violations == 16 and p.max_polish_rounds == 3
 
 
 def test_error_codes_and_messages(rg_lib):
