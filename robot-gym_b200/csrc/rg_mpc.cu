@@ -38,11 +38,13 @@ extern "C" int rg_debug_set_trace(double* dev_buf, int env) {
 #define RG_TRACE(slot, value) do { if (g_trace && env == g_trace_env && threadIdx.x == 0) g_trace[slot] = (value); } while (0)
 // phase timers: cycles accumulated in g_trace[900 + phase] by thread 0 of the traced env
 #define RG_TIC() long long rg_t0_ = clock64()
+#define RG_TOCL(phase, thr) do { if (g_trace && (int)blockIdx.x == g_trace_env && threadIdx.x == (thr)) g_trace[900 + (phase)] += (double)(clock64() - rg_t0_); rg_t0_ = clock64(); } while (0)
 #define RG_TOC(phase) do { if (g_trace && (int)blockIdx.x == g_trace_env && threadIdx.x == 0) g_trace[900 + (phase)] += (double)(clock64() - rg_t0_); rg_t0_ = clock64(); } while (0)
 #else
 #define RG_TRACE(slot, value) do { } while (0)
 #define RG_TIC() do { } while (0)
 #define RG_TOC(phase) do { } while (0)
+#define RG_TOCL(phase, thr) do { } while (0)
 #endif
 
 namespace {
@@ -164,15 +166,19 @@ __device__ __forceinline__ double quad_sum(double v) {   // sum over the 4 legs 
 // -> 2 barriers per 4 columns and ~2.6 instructions per useful FMA instead of 60 barriers and ~5.5.
 // The factor's diagonal lives in sm.rdiag as 1 / L[j][j]; the triangular sweeps need nothing else.
 // __noinline__: one copy of the code, called from every phase of the solver.
+// j_begin (a multiple of 4): columns before it already hold the factor and are kept -- a matrix that
+// changed only in rows/columns >= j_begin has the same leading factor columns (left-looking order).
 template <int H>
-__device__ __noinline__ void cholesky_rows(Smem<H>& sm) {
+__device__ __noinline__ void cholesky_rows(Smem<H>& sm, int j_begin) {
   constexpr int N6 = Cfg<H>::N6;
   const int i = threadIdx.x;
   const bool row_ok = i < N6;
   double* row_i = sm.psi + prow(row_ok ? i : 0);
   if (i == 0) sm.flag = 0;   // published by the first barrier below
+  RG_TIC();
 #pragma unroll 1
-  for (int j0 = 0; j0 < N6; j0 += 4) {
+  for (int j0 = j_begin; j0 < N6; j0 += 4) {
+    RG_TOCL(32, N6 - 1);
     const int w = N6 - j0 < 4 ? N6 - j0 : 4;          // panel width (the last panel of N6 = 30 has 2 columns)
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     const bool in_play = row_ok && i >= j0;
@@ -205,7 +211,9 @@ __device__ __noinline__ void cholesky_rows(Smem<H>& sm) {
         for (int c = 0; c < 4; ++c) if (j0 + c <= i) sm.blk44[4 * (i - j0) + c] = acc[c];
       }
     }
+    RG_TOCL(30, N6 - 1);
     __syncthreads();
+    RG_TOCL(33, N6 - 1);
     if (in_play) {
       // 4x4 diagonal block A' (lower triangle), broadcast loads; entries beyond the panel width read as identity
       double a[4][4];
@@ -258,79 +266,110 @@ __device__ __noinline__ void cholesky_rows(Smem<H>& sm) {
         for (int c = 0; c < 4; ++c) if (c < w) row_i[j0 + c] = x[c];
       }
     }
+    RG_TOCL(31, N6 - 1);
     __syncthreads();
   }
 }
 
 // ---- Psi x = b with the factor, b/x in sm.avec; executed by warp 0 only ----------------------
-// Each lane owns rows lane, lane+32, ...; the pivot value travels by __shfl, no block barrier.
-// (Tried and measured slower under load: 4x4-blocked sweeps with precomputed block inverses, and
-// register prefetch of the next column -- other resident warps already hide the shared-memory latency.)
+// Each lane owns RPL CONSECUTIVE rows (30 lanes x 1, 2 or 4 rows).  One step eliminates the RPL pivots
+// of one lane: a lane-local RPL x RPL triangular solve with the own diagonal reciprocals held in
+// registers, RPL shuffles in flight together, then RPL FMAs per owned row -- all predicated, no
+// divergent branch and no shared-memory load on the pivot chain.  (tools/microbench/chol_bench.cu:
+// 8.7-9.3k cycles per solve alone on an SM against 14.8k for one-pivot-per-step with strided rows.)
+// T(i) mod 16 is a permutation over the even and over the odd rows of 16 consecutive lanes, so the
+// per-column loads stay bank-conflict free with this ownership too.
 template <int H>
 __device__ __noinline__ void tri_solve_warp0(Smem<H>& sm) {
   constexpr int N6 = Cfg<H>::N6;
   constexpr int RPL = Cfg<H>::RPL;
+  constexpr int NL = N6 / RPL;
+  static_assert(NL * RPL == N6 && NL <= 32, "rows must split evenly over the lanes of one warp");
   const int lane = threadIdx.x;   // caller guarantees threadIdx.x < 32
-  double x[RPL];
-  int base[RPL];
+  const bool active = lane < NL;
+  const int i0 = active ? lane * RPL : 0;
+  double x[RPL], rd[RPL], lb[RPL][RPL], l[RPL][RPL];
+  const double* rowp[RPL];
 #pragma unroll
   for (int r = 0; r < RPL; ++r) {
-    const int i = lane + 32 * r;
-    x[r] = i < N6 ? sm.avec[i] : 0.0;
-    base[r] = prow(i < N6 ? i : 0);
+    x[r] = active ? sm.avec[i0 + r] : 0.0;
+    rd[r] = sm.rdiag[i0 + r];
+    rowp[r] = sm.psi + prow(i0 + r);
+#pragma unroll
+    for (int c = 0; c < r; ++c) lb[r][c] = rowp[r][i0 + c];
   }
   // forward: L y = b
-#pragma unroll
-  for (int slot = 0; slot < RPL; ++slot) {
-    const int jend = N6 - 32 * slot < 32 ? N6 - 32 * slot : 32;
 #pragma unroll 1
-    for (int jj = 0; jj < jend; ++jj) {
-      const int j = 32 * slot + jj;
-      double xj = x[slot] * sm.rdiag[j];
-      xj = __shfl_sync(kFull, xj, jj);
-      if (lane == jj) x[slot] = xj;
+  for (int p = 0; p < NL; ++p) {
 #pragma unroll
-      for (int r = slot; r < RPL; ++r) {
-        const int i = lane + 32 * r;
-        if (i > j && i < N6) x[r] = fma(-sm.psi[base[r] + j], xj, x[r]);
-      }
+    for (int r = 0; r < RPL; ++r)
+#pragma unroll
+      for (int c = 0; c < RPL; ++c) l[r][c] = rowp[r][p * RPL + c];   // lanes <= p read past their diagonal: value unused
+    double y[RPL], yb[RPL];
+#pragma unroll
+    for (int c = 0; c < RPL; ++c) {
+      double v = x[c];
+#pragma unroll
+      for (int cc = 0; cc < c; ++cc) v = fma(-lb[c][cc], y[cc], v);
+      y[c] = v * rd[c];
     }
+#pragma unroll
+    for (int c = 0; c < RPL; ++c) yb[c] = __shfl_sync(kFull, y[c], p);
+    const bool own = lane == p, later = lane > p;
+#pragma unroll
+    for (int c = 0; c < RPL; ++c)
+#pragma unroll
+      for (int r = 0; r < RPL; ++r) x[r] = fma(later ? -l[r][c] : 0.0, yb[c], x[r]);
+#pragma unroll
+    for (int c = 0; c < RPL; ++c) x[c] = own ? y[c] : x[c];
   }
   // backward: L^T x = y
-#pragma unroll
-  for (int slot = RPL - 1; slot >= 0; --slot) {
-    const int jend = N6 - 32 * slot < 32 ? N6 - 32 * slot : 32;
 #pragma unroll 1
-    for (int jj = jend - 1; jj >= 0; --jj) {
-      const int j = 32 * slot + jj;
-      double xj = x[slot] * sm.rdiag[j];
-      xj = __shfl_sync(kFull, xj, jj);
-      if (lane == jj) x[slot] = xj;
-      const double* row_j = sm.psi + prow(j);
+  for (int p = NL - 1; p >= 0; --p) {
 #pragma unroll
-      for (int r = 0; r <= slot; ++r) {
-        const int i = lane + 32 * r;
-        if (i < j) x[r] = fma(-row_j[i], xj, x[r]);
-      }
+    for (int c = 0; c < RPL; ++c) {
+      const double* rp = sm.psi + prow(p * RPL + c) + i0;           // row of the pivot, my columns
+#pragma unroll
+      for (int r = 0; r < RPL; ++r) l[c][r] = rp[r];
     }
-  }
+    double z[RPL], zb[RPL];
 #pragma unroll
-  for (int r = 0; r < RPL; ++r) { const int i = lane + 32 * r; if (i < N6) sm.avec[i] = x[r]; }
+    for (int c = RPL - 1; c >= 0; --c) {
+      double v = x[c];
+#pragma unroll
+      for (int cc = c + 1; cc < RPL; ++cc) v = fma(-lb[cc][c], z[cc], v);
+      z[c] = v * rd[c];
+    }
+#pragma unroll
+    for (int c = 0; c < RPL; ++c) zb[c] = __shfl_sync(kFull, z[c], p);
+    const bool own = lane == p, earlier = lane < p;
+#pragma unroll
+    for (int c = RPL - 1; c >= 0; --c)
+#pragma unroll
+      for (int r = 0; r < RPL; ++r) x[r] = fma(earlier ? -l[c][r] : 0.0, zb[c], x[r]);
+#pragma unroll
+    for (int c = 0; c < RPL; ++c) x[c] = own ? z[c] : x[c];
+  }
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) sm.avec[i0 + r] = x[r];
+  }
 }
 
 // Row p of Psi := scale * K^-1[p][:] + (diagonal 6x6 block of sm.nblk), thread per row.
+// Only the time blocks >= t_begin (rows and columns) are written; the rest keeps the factor.
 template <int H>
-__device__ __forceinline__ void psi_build_rows(Smem<H>& sm, const RgMpcDev* __restrict__ ws) {
+__device__ __forceinline__ void psi_build_rows(Smem<H>& sm, const RgMpcDev* __restrict__ ws, int t_begin) {
   constexpr int N6 = Cfg<H>::N6;
   const int p = threadIdx.x;
-  if (p < N6) {
+  if (p < N6 && p >= 6 * t_begin) {
     const int j = p / 6, c = p - 6 * j;
     double* row = sm.psi + prow(p);
     // K^-1 couples channel c with the three angular channels (c < 3) or only with itself (c >= 3)
     if (c < 3) {
       const double* ka = sm.kinv_ang + tri(3 * j + c, 0);
 #pragma unroll 2
-      for (int k = 0; k < j; ++k) {
+      for (int k = t_begin; k < j; ++k) {
         double* dst = row + 6 * k;
         const double v0 = ka[3 * k], v1 = ka[3 * k + 1], v2 = ka[3 * k + 2];
         dst[0] = v0; dst[1] = v1; dst[2] = v2; dst[3] = 0.0; dst[4] = 0.0; dst[5] = 0.0;
@@ -338,7 +377,7 @@ __device__ __forceinline__ void psi_build_rows(Smem<H>& sm, const RgMpcDev* __re
     } else {
       const double* kl = ws->kinv_lin[c - 3] + tri(j, 0);
 #pragma unroll 2
-      for (int k = 0; k < j; ++k) {
+      for (int k = t_begin; k < j; ++k) {
         double* dst = row + 6 * k;
         const double v = kl[k];
         dst[0] = 0.0; dst[1] = 0.0; dst[2] = 0.0;
@@ -471,7 +510,10 @@ __device__ __forceinline__ void apply_p(Smem<H>& sm, const RgMpcDev* __restrict_
 // Psi = K^-1 + sum_legs B M B^T (M = per-block symmetric 3x3, packed xx,yy,zz,xz,yz,xy), then its
 // Cholesky factor.  All threads call.
 template <int H>
-__device__ __forceinline__ void factor_psi(Smem<H>& sm, const RgMpcDev* __restrict__ ws, const Blk& b, const double* m) {
+// t_begin (even): time blocks before it are unchanged since the previous factorisation, whose leading
+// 6 t_begin columns are reused (6 t_begin is a multiple of the Cholesky panel width).
+__device__ __forceinline__ void factor_psi(Smem<H>& sm, const RgMpcDev* __restrict__ ws, const Blk& b, const double* m, int t_begin = 0) {
+  RG_TIC();
   double am[9];   // A M
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
@@ -501,11 +543,11 @@ __device__ __forceinline__ void factor_psi(Smem<H>& sm, const RgMpcDev* __restri
     for (int i = 0; i < 21; ++i) sm.nblk[b.t][i] = n[i];
   }
   __syncthreads();
-  RG_TIC();
-  psi_build_rows<H>(sm, ws);
+  RG_TOC(12);
+  psi_build_rows<H>(sm, ws, t_begin);
   __syncthreads();
   RG_TOC(10);
-  cholesky_rows<H>(sm);
+  cholesky_rows<H>(sm, 6 * t_begin);
   RG_TOC(11);
 }
 
@@ -618,6 +660,9 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   const int env = blockIdx.x;
   if (env >= n_env) return;
   const int tid = threadIdx.x;
+#ifdef RG_DEBUG_TRACE
+  const long long rg_tstart_ = clock64();
+#endif
   const int t_blk = tid >> 2, leg = tid & 3;
   const bool is_blk = tid < C::NB;
 
@@ -791,6 +836,9 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   __syncthreads();
 
   RG_TIC();
+#ifdef RG_DEBUG_TRACE
+  if (g_trace && (int)blockIdx.x == g_trace_env && threadIdx.x == 0) g_trace[900 + 8] += (double)(clock64() - rg_tstart_);
+#endif
   // ---------------------------------------------------------------- per-block constants
   Blk blk;
 #pragma unroll
@@ -1012,7 +1060,9 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 #pragma unroll
       for (int r = 0; r < 10; ++r) if (active_blk && lam[r] > 0.03 * s[r]) act |= 1u << r;
     }
-    bool polished = false;
+    bool polished = false, fact_valid = false;   // the factor in shared memory is the interior point's, if any
+    unsigned act_fact = 0;
+    double prev_nchg = 1e300;
     double up[3] = {0.0, 0.0, 0.0};
     // 3, 6, 12 rounds: later attempts start from a sharper guess; a dead interior point gets the full budget
     const int round_budget = cold ? cold_rounds : ipm_dead ? (max_polish << 2) : (max_polish << attempt);
@@ -1077,7 +1127,22 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       const double inv2a = 1.0 / two_alpha;
 #pragma unroll
       for (int i = 0; i < 6; ++i) mproj[i] *= inv2a;
-      factor_psi<H>(sm, ws, blk, mproj);
+      RG_TOC(20);
+      // Only the time steps from the first block whose active set moved since the last factorisation
+      // change Psi, and a left-looking Cholesky keeps its leading columns: refactor the tail only
+      // (active rows cluster at the end of the horizon: DESIGN.md 3.7).
+      {
+        double dsum = 0.0, dmx = 0.0, tmin = (double)H;
+        if (active_blk && act != act_fact) tmin = (double)t_blk;
+        if (!fact_valid) tmin = 0.0;
+        block_reduce<C::NW>(dsum, dmx, tmin, sm.red);
+        if (tmin < (double)H) factor_psi<H>(sm, ws, blk, mproj, ((int)tmin) & ~1);
+        else if (tid == 0) sm.flag = 0;
+        act_fact = act;
+        fact_valid = true;
+        __syncthreads();
+      }
+      RG_TIC();
       if (sm.flag) {
         if (!cold) { status |= RG_STATUS_NUMERIC; ipm_dead = true; }   // a failed cold start just hands over
         break;
@@ -1100,18 +1165,21 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       // each: when it moves after pass 0 the refinement would be wasted (the next round starts over),
       // and it is skipped as well when pass 0 already left a projected gradient at rounding level.
       unsigned act_new = act;
-      double nchg = 0.0, pgm = 0.0;
+      double nchg = 0.0, ncone = 0.0, pgm = 0.0;
       bool accept = false;
 #pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {
         double ng[3], bprime[3], dx[3], pu[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) ng[d] = -gr[d];
+        RG_TOC(21);
         woodbury_solve<H>(sm, blk, mproj, ng, bprime);
+        RG_TOC(22);
         sym3_mul(mproj, bprime, dx);
 #pragma unroll
         for (int d = 0; d < 3; ++d) up[d] += dx[d];
         apply_p<H>(sm, ws, blk, up, pu);
+        RG_TOC(23);
 #pragma unroll
         for (int d = 0; d < 3; ++d) gr[d] = pu[d] + q[d];
 
@@ -1146,9 +1214,14 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
         double pg[3];
         sym3_mul(mproj, gr, pg);
         pgm = active_blk ? two_alpha * fmax(fabs(pg[0]), fmax(fabs(pg[1]), fabs(pg[2]))) : 0.0;
-        nchg = (double)__popc(act_new ^ act);
+        // one reduction carries both counts: rows that moved, and how many of those are friction-cone rows
+        // (bits 0-3 / 5-8; bits 4 / 9 are the fz bounds)
+        nchg = (double)(__popc(act_new ^ act) + 4096 * __popc((act_new ^ act) & 0x1EFu));
         double dmn = 0.0;
         block_reduce<C::NW>(nchg, pgm, dmn, sm.red);
+        ncone = floor(nchg * (1.0 / 4096.0));
+        nchg -= 4096.0 * ncone;
+        RG_TOC(24);
         if (nchg > 0.0) break;
         if (pgm <= (pass == 0 ? RG_SKIP_REFINE_TOL : 1e-7) * qscale) { accept = true; break; }
       }
@@ -1161,8 +1234,10 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       }
 #endif
       if (accept) { polished = true; break; }
-      // too many rows violated by the unconstrained minimiser: the interior point is the better tool
-      if (cold && round == 0 && nchg > cold_max_viol) break;
+      // the cold start hands over to the interior point when the unconstrained minimiser violates too
+      // many friction-cone rows (fz-bound rows settle in a round or two, cone rows make it cycle), or when the number of rows that move stops shrinking (the iteration is cycling)
+      if (cold && ((round == 0 && ncone > cold_max_viol) || (round >= 1 && nchg >= prev_nchg && nchg > 2.0))) break;
+      prev_nchg = nchg;
       act = act_new;
     }
     if (polished) {
@@ -1185,6 +1260,9 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   }
 
   RG_TOC(7);
+#ifdef RG_DEBUG_TRACE
+  if (g_trace && (int)blockIdx.x == g_trace_env && threadIdx.x == 0) g_trace[900 + 9] += (double)(clock64() - rg_tstart_);
+#endif
   // ---------------------------------------------------------------- outputs (negated solution)
   if (is_blk) {
     const float fx = active_blk ? (float)(-u_out[0]) : 0.f;
@@ -1252,7 +1330,7 @@ __global__ void __launch_bounds__(Cfg<H>::NT) chol_selftest_kernel(const double*
     sm.avec[tid] = rhs[tid];
   }
   __syncthreads();
-  cholesky_rows<H>(sm);
+  cholesky_rows<H>(sm, 0);
   if (tid < 32) tri_solve_warp0<H>(sm);
   __syncthreads();
   if (tid < N6) {
