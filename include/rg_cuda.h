@@ -86,7 +86,7 @@ typedef struct rg_mpc_params {
   int32_t max_ipm_iters;       /* hard cap (40) */
   int32_t max_polish_rounds;   /* 0 disables the active-set polish; rounds per attempt (3) */
   int32_t cold_start_rounds;   /* active-set rounds tried from the unconstrained minimiser BEFORE the
-                                  interior point (8; it also stops as soon as the number of
+                                  interior point (5; it also stops as soon as the number of
                                   rows that move stops shrinking); 0 = always run the interior point first */
   int32_t cold_start_max_violations; /* give the cold start up at once when the unconstrained minimiser
                                   violates more friction-cone rows than this (16 * horizon / 10) */

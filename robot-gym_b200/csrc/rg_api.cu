@@ -181,7 +181,7 @@ extern "C" int rg_mpc_default_params(rg_mpc_params* p, double mass, const double
   p->ipm_tol = 1e-6;
   p->max_ipm_iters = 40;
   p->max_polish_rounds = 3;
-  p->cold_start_rounds = 8;
+  p->cold_start_rounds = 5;
   p->cold_start_max_violations = horizon > 0 ? (16 * horizon + 9) / 10 : 16;
   return RG_OK;
 }

@@ -125,6 +125,18 @@ __device__ __forceinline__ double c2f(int h, int j, int k) {
 // After the first solve of an active-set round the refinement pass is skipped when the projected
 // gradient is already below this (relative to the gradient scale): the error it leaves in the
 // weakly curved directions is <= tol / (2 alpha).
+#ifndef RG_IPM_LAM0
+#define RG_IPM_LAM0 0.01
+#endif
+// Interior-point start (used only when the cold start gives up; A/B in tools/ab_gaits.py):
+//   mu0 = RG_IPM_LAM0 * max(|q|, RG_IPM_RD_SCALE * |P u0 + q|)   centred start s lam = mu0
+//   u0  = safe point + RG_IPM_WARM * (largest strictly feasible step towards the last active-set iterate)
+#ifndef RG_IPM_RD_SCALE
+#define RG_IPM_RD_SCALE 1.0
+#endif
+#ifndef RG_IPM_WARM
+#define RG_IPM_WARM 0.99
+#endif
 #ifndef RG_SKIP_REFINE_TOL
 #define RG_SKIP_REFINE_TOL 1e-11
 #endif
@@ -662,6 +674,13 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   const int tid = threadIdx.x;
 #ifdef RG_DEBUG_TRACE
   const long long rg_tstart_ = clock64();
+  // timeline mode (trace env == -2): per-CTA start / end in ns and the SM id, 4 doubles per env after slot 1024
+  if (g_trace && g_trace_env == -2 && tid == 0) {
+    unsigned long long ns; unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_trace[1024 + 4 * env] = (double)ns; g_trace[1024 + 4 * env + 2] = (double)smid;
+  }
 #endif
   const int t_blk = tid >> 2, leg = tid & 3;
   const bool is_blk = tid < C::NB;
@@ -883,7 +902,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
       if (!active_blk) s[r] = 1.0;
-      lam[r] = active_blk ? 0.01 * qscale / s[r] : 1.0;   // inactive threads carry harmless 1/1 pairs
+      lam[r] = active_blk ? RG_IPM_LAM0 * qscale / s[r] : 1.0;   // inactive threads carry harmless 1/1 pairs
     }
   }
   const double m_total = 10.0 * H * n_stance;
@@ -913,6 +932,21 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     bool converged = false, ipm_dead = false;
     const bool cold = attempt < 0;
     if (!cold) {
+    if (iters == 0) {
+      // Centred start s lam = mu0 with mu0 commensurate with the dual residual at the start: with mu0 far
+      // below |r_d| the first iterations crawl along the boundary (pace / bound problems: |r_d| ~ 100 |q|).
+      double pu0[3];
+      apply_p<H>(sm, ws, blk, u, pu0);
+      double dsum = 0.0, rd0 = 0.0, dmn = 0.0;
+      if (active_blk) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) rd0 = fmax(rd0, fabs(pu0[d] + q[d]));
+      }
+      block_reduce<C::NW>(dsum, rd0, dmn, sm.red);
+      const double mu0 = RG_IPM_LAM0 * fmax(qscale, RG_IPM_RD_SCALE * rd0);
+#pragma unroll
+      for (int r = 0; r < 10; ++r) lam[r] = active_blk ? mu0 / s[r] : 1.0;
+    }
 #pragma unroll 1
     while (true) {
       double pu[3], rd[3], gl[3];
@@ -1251,7 +1285,33 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       break;
     }
     if (ipm_dead) break;
-    if (cold) continue;
+    if (cold) {
+      // The cold start gave up: move the interior point's start from the safe point towards the last
+      // active-set iterate, as far as strict feasibility allows (ratio test), keeping r_p = 0.
+      double dir[3] = {up[0] - u[0], up[1] - u[1], up[2] - u[2]}, c5d[5];
+      g_mul(dir, mu, c5d);
+      double dsum = 0.0, dmx = 0.0, thmax = 1.0;
+      if (active_blk) {
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          if (c5d[r] > 0.0) thmax = fmin(thmax, s[r] / c5d[r]);
+          if (c5d[r] < 0.0) thmax = fmin(thmax, s[5 + r] / -c5d[r]);
+        }
+        if (!(thmax == thmax)) thmax = 0.0;
+      }
+      block_reduce<C::NW>(dsum, dmx, thmax, sm.red);
+      const double theta = RG_IPM_WARM * thmax;
+      if (active_blk && theta > 0.0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) u[d] += theta * dir[d];
+        double c5[5];
+        g_mul(u, mu, c5);
+#pragma unroll
+        for (int r = 0; r < 5; ++r) { s[r] = hv_up[r] - c5[r]; s[5 + r] = c5[r] - lo_b[r]; }
+#pragma unroll
+      }
+      continue;
+    }
     tol = fmax(tol * 1e-2, 1e-9);   // float64 interior-point iterates are trustworthy down to ~1e-9 here
   }
   if (!done) {
@@ -1262,6 +1322,11 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   RG_TOC(7);
 #ifdef RG_DEBUG_TRACE
   if (g_trace && (int)blockIdx.x == g_trace_env && threadIdx.x == 0) g_trace[900 + 9] += (double)(clock64() - rg_tstart_);
+  if (g_trace && g_trace_env == -2 && tid == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    g_trace[1024 + 4 * env + 1] = (double)ns;
+  }
 #endif
   // ---------------------------------------------------------------- outputs (negated solution)
   if (is_blk) {

@@ -380,6 +380,152 @@ void run(const char* name, const double* d_a, const std::vector<double>& l_ref, 
 }
 
 
+
+// ---------------------------------------------------------------- V7: square layout, rows 16-byte aligned (stride LD, LD/2 odd):
+// every shared-memory load of phase 1 is 128-bit (own row conflict-free per quarter warp, panel rows broadcast)
+template <int N6, int W, int LD, int UNROLL>
+__device__ __noinline__ void chol_sq(double* psi, double* rdiag, double* blk, int* flag) {
+  const int i = threadIdx.x;
+  const bool row_ok = i < N6;
+  double* row_i = psi + (row_ok ? i : 0) * LD;
+  if (i == 0) *flag = 0;
+#pragma unroll 1
+  for (int j0 = 0; j0 < N6; j0 += W) {
+    const int w = N6 - j0 < W ? N6 - j0 : W;
+    double acc[W];
+    const bool in_play = row_ok && i >= j0;
+    if (in_play) {
+      const double* p[W];
+#pragma unroll
+      for (int c = 0; c < W; ++c) {
+        p[c] = psi + (j0 + (c < w ? c : 0)) * LD;
+        acc[c] = (c < w && j0 + c <= i) ? row_i[j0 + c] : 0.0;
+      }
+#pragma unroll UNROLL
+      for (int k = 0; k < j0; k += 2) {
+        const double2 a = *reinterpret_cast<const double2*>(row_i + k);
+#pragma unroll
+        for (int c = 0; c < W; ++c) {
+          const double2 b = *reinterpret_cast<const double2*>(p[c] + k);
+          acc[c] = fma(-a.x, b.x, acc[c]);
+          acc[c] = fma(-a.y, b.y, acc[c]);
+        }
+      }
+      if (i < j0 + w) {
+#pragma unroll
+        for (int c = 0; c < W; ++c) if (j0 + c <= i) blk[W * (i - j0) + c] = acc[c];
+      }
+    }
+    __syncthreads();
+    if (in_play) {
+      double a[W][W];
+#pragma unroll
+      for (int r = 0; r < W; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) a[r][c] = (r < w) ? blk[W * r + c] : (r == c ? 1.0 : 0.0);
+      double rd[W];
+      bool bad = false;
+#pragma unroll
+      for (int c = 0; c < W; ++c) {
+        double d = a[c][c];
+        if (!(d > 0.0)) { bad = true; d = 1e-300; }
+        rd[c] = rsqrt(d);
+#pragma unroll
+        for (int r = c + 1; r < W; ++r) a[r][c] *= rd[c];
+#pragma unroll
+        for (int r = c + 1; r < W; ++r)
+#pragma unroll
+          for (int cc = c + 1; cc <= r; ++cc) a[r][cc] = fma(-a[r][c], a[cc][c], a[r][cc]);
+      }
+      if (i < j0 + w) {
+        const int r = i - j0;
+#pragma unroll
+        for (int rr = 0; rr < W; ++rr) {
+          if (rr == r) {
+#pragma unroll
+            for (int c = 0; c < rr; ++c) row_i[j0 + c] = a[rr][c];
+            rdiag[i] = rd[rr];
+          }
+        }
+        if (bad && r == 0) *flag = 1;
+      } else {
+        double x[W];
+#pragma unroll
+        for (int c = 0; c < W; ++c) {
+          double v = acc[c];
+#pragma unroll
+          for (int k = 0; k < c; ++k) v = fma(-x[k], a[c][k], v);
+          x[c] = v * rd[c];
+        }
+#pragma unroll
+        for (int c = 0; c < W; ++c) if (c < w) row_i[j0 + c] = x[c];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int N6, int VARIANT>
+__global__ void __launch_bounds__(((N6 + 31) / 32) * 32, 4)
+bench_sq_kernel(const double* __restrict__ a_dense, double* __restrict__ l_out, long long* __restrict__ cycles, int reps) {
+  constexpr int LD = N6 + 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* psi = reinterpret_cast<double*>(smem_raw);
+  double* rdiag = psi + N6 * LD;
+  double* blk = rdiag + N6;
+  int* flag = reinterpret_cast<int*>(blk + 64);
+  const int tid = threadIdx.x;
+  long long total = 0;
+  for (int rep = 0; rep < reps; ++rep) {
+    if (tid < N6)
+      for (int k = 0; k <= tid; ++k) psi[tid * LD + k] = a_dense[tid * N6 + k];
+    __syncthreads();
+    const long long t0 = clock64();
+    if (VARIANT == 0) chol_sq<N6, 4, LD, 2>(psi, rdiag, blk, flag);
+    if (VARIANT == 1) chol_sq<N6, 6, LD, 2>(psi, rdiag, blk, flag);
+    if (VARIANT == 2) chol_sq<N6, 4, LD, 4>(psi, rdiag, blk, flag);
+    total += clock64() - t0;
+    __syncthreads();
+  }
+  if (blockIdx.x == 0) {
+    if (tid == 0) cycles[0] = total / reps;
+    if (tid < N6) {
+      for (int k = 0; k < tid; ++k) l_out[tid * N6 + k] = psi[tid * LD + k];
+      l_out[tid * N6 + tid] = 1.0 / rdiag[tid];
+    }
+  }
+}
+
+template <int N6, int VARIANT>
+void run_sq(const char* name, const double* d_a, const std::vector<double>& l_ref, double* d_l, long long* d_cyc) {
+  const int nt = ((N6 + 31) / 32) * 32;
+  const size_t smem = (N6 * (N6 + 2) + N6 + 64 + 2) * sizeof(double);
+  cudaFuncSetAttribute(bench_sq_kernel<N6, VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(bench_sq_kernel<N6, VARIANT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  const int reps = 20;
+  bench_sq_kernel<N6, VARIANT><<<1, nt, smem>>>(d_a, d_l, d_cyc, reps);
+  bench_sq_kernel<N6, VARIANT><<<1, nt, smem>>>(d_a, d_l, d_cyc, reps);
+  cudaDeviceSynchronize();
+  long long solo = 0;
+  cudaMemcpy(&solo, d_cyc, sizeof(solo), cudaMemcpyDeviceToHost);
+  std::vector<double> l(N6 * N6);
+  cudaMemcpy(l.data(), d_l, sizeof(double) * N6 * N6, cudaMemcpyDeviceToHost);
+  double err = 0.0;
+  for (int i = 0; i < N6; ++i) for (int k = 0; k <= i; ++k) err = fmax(err, fabs(l[i * N6 + k] - l_ref[i * N6 + k]));
+  const int grid = 148 * 7 * 4;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  bench_sq_kernel<N6, VARIANT><<<grid, nt, smem>>>(d_a, d_l, d_cyc, reps);
+  cudaEventRecord(e0);
+  bench_sq_kernel<N6, VARIANT><<<grid, nt, smem>>>(d_a, d_l, d_cyc, reps);
+  cudaEventRecord(e1); cudaDeviceSynchronize();
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  long long loaded = 0;
+  cudaMemcpy(&loaded, d_cyc, sizeof(loaded), cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaGetLastError();
+  printf("N=%3d %-34s solo %7lld cyc | loaded (smem-limited CTAs/SM) %7lld cyc/CTA, %6.2f M factorisations/s | max|L-Lref| %.2e %s\n",
+         N6, name, solo, loaded, grid * (double)reps / ms * 1e-3, err, e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
 // ================================================================ triangular solves  Psi x = b  (warp 0 only)
 // T0: the kernel's current routine: lane owns rows lane, lane+32, ...; one pivot per step
 template <int N6>
@@ -674,6 +820,9 @@ void run_all() {
   run<N6, 4>("panel W=8 unroll 1", d_a, l, d_l, d_cyc);
   run<N6, 5>("panel W=2 unroll 4", d_a, l, d_l, d_cyc);
   run<N6, 6>("DMMA m8n8k4 update, W=8", d_a, l, d_l, d_cyc);
+  run_sq<N6, 0>("square LD=N+2, LDS.128, W=4 u2", d_a, l, d_l, d_cyc);
+  run_sq<N6, 1>("square LD=N+2, LDS.128, W=6 u2", d_a, l, d_l, d_cyc);
+  run_sq<N6, 2>("square LD=N+2, LDS.128, W=4 u4", d_a, l, d_l, d_cyc);
   {
     std::vector<double> b(N6), y(N6), x(N6);
     for (auto& v : b) v = rand() / (double)RAND_MAX - 0.5;

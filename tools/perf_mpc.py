@@ -17,6 +17,9 @@ def main():
     ctrl = GHOST.GetCtrlConstants()
     for horizon in (10,):
         p = rg.default_mpc_params(ctrl.MPC_BODY_MASS, ctrl.MPC_BODY_INERTIA, ctrl.MPC_BODY_HEIGHT, horizon)
+        for kv in filter(None, os.environ.get("RG_PERF_PARAMS", "").split(",")):     # e.g. ipm_tol=1e-4,cold_start_rounds=0
+            k, v = kv.split("=")
+            setattr(p, k, type(getattr(p, k))(float(v)))
         ws = rg.MpcWorkspace(p)
         for n in sizes:
             for all_stance in (False, True):

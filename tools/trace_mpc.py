@@ -29,13 +29,14 @@ def main():
     ctrl = GHOST.GetCtrlConstants()
     p = rg.default_mpc_params(ctrl.MPC_BODY_MASS, ctrl.MPC_BODY_INERTIA, ctrl.MPC_BODY_HEIGHT, 10)
     ws = rg.MpcWorkspace(p)
-    n = 65536
-    st = synthetic.make_states(n, GHOST)
+    n = int(os.environ.get("RG_TRACE_N", "65536"))     # batch the env index refers to (make_states(n) draws depend on n)
+    gait = os.environ.get("RG_TRACE_GAIT", "trot")
+    st = synthetic.make_states(n, GHOST if gait == "trot" else with_gait(GHOST, gait))
     t = lambda a: torch.from_numpy(a).cuda()
     full = (t(st.com_velocity_body), t(st.base_rpy), t(st.base_rpy_rate), t(st.planned_contacts), t(st.foot_positions_base), t(st.command))
     trace = torch.zeros(1024, dtype=torch.float64, device="cuda")
     for e in envs:
-        for label, lo, cnt, idx in (("solo", e, 1, 0), ("loaded", 0, n, e)):
+        for label, lo, cnt, idx in (("solo", e, 1, 0), ("loaded", 0, n, e))[:1 if os.environ.get("RG_TRACE_SOLO") else 2]:
             args = tuple(a[lo:lo + cnt].contiguous() for a in full)
             lib.rg_debug_set_trace(None, -1)
             for _ in range(2): f, _, info = rg.mpc_build_solve(ws, *args)
@@ -47,7 +48,7 @@ def main():
             tr = trace.cpu().numpy(); inf = info.cpu().numpy()[idx]
             tot = tr[909]
             print(f"env {e} [{label}] iters {inf[0]} rounds {inf[1]} status {inf[2]} nact {inf[3]}: total {tot:.0f} cyc = {tot/1.965e3:.1f} us")
-            for r in range(16):
+            for r in range(64):
                 if tr[4 * r] == 0 and tr[4 * r + 1] == 0 and r > 0: break
                 kind = {-1.0: "as round (after ipm)", -2.0: "as round (cold)"}.get(tr[4 * r], "ipm iter")
                 print(f"    trace[{r}] {kind}: {tr[4*r]:.3e} {tr[4*r+1]:.3e} {tr[4*r+2]:.3e} {tr[4*r+3]:.3e}")
