@@ -134,6 +134,13 @@ __device__ __forceinline__ double c2f(int h, int j, int k) {
 #ifndef RG_IPM_RD_SCALE
 #define RG_IPM_RD_SCALE 1.0
 #endif
+// cold start: rounds granted beyond cold_start_rounds while at most this many rows still move
+#ifndef RG_COLD_EXTEND_ROUNDS
+#define RG_COLD_EXTEND_ROUNDS 0
+#endif
+#ifndef RG_COLD_EXTEND_NCHG
+#define RG_COLD_EXTEND_NCHG 4.0
+#endif
 #ifndef RG_IPM_WARM
 #define RG_IPM_WARM 0.99
 #endif
@@ -1099,7 +1106,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     double prev_nchg = 1e300;
     double up[3] = {0.0, 0.0, 0.0};
     // 3, 6, 12 rounds: later attempts start from a sharper guess; a dead interior point gets the full budget
-    const int round_budget = cold ? cold_rounds : ipm_dead ? (max_polish << 2) : (max_polish << attempt);
+    const int round_budget = cold ? cold_rounds + RG_COLD_EXTEND_ROUNDS : ipm_dead ? (max_polish << 2) : (max_polish << attempt);
 #pragma unroll 1
     for (int round = 0; round < round_budget; ++round) {
       ++polish_rounds;
@@ -1270,7 +1277,9 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       if (accept) { polished = true; break; }
       // the cold start hands over to the interior point when the unconstrained minimiser violates too
       // many friction-cone rows (fz-bound rows settle in a round or two, cone rows make it cycle), or when the number of rows that move stops shrinking (the iteration is cycling)
-      if (cold && ((round == 0 && ncone > cold_max_viol) || (round >= 1 && nchg >= prev_nchg && nchg > 2.0))) break;
+      // (past the nominal budget only an almost-settled iteration -- <= RG_COLD_EXTEND_NCHG rows still moving -- goes on)
+      if (cold && ((round == 0 && ncone > cold_max_viol) || (round >= 1 && nchg >= prev_nchg && nchg > 2.0) ||
+                   (round + 1 >= cold_rounds && nchg > RG_COLD_EXTEND_NCHG))) break;
       prev_nchg = nchg;
       act = act_new;
     }
