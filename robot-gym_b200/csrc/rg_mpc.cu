@@ -134,6 +134,10 @@ __device__ __forceinline__ double c2f(int h, int j, int k) {
 #ifndef RG_IPM_RD_SCALE
 #define RG_IPM_RD_SCALE 1.0
 #endif
+// cold start: fz >= fz_min is guessed active in the last RG_COLD_GUESS_LAST steps of the horizon (0 = empty set)
+#ifndef RG_COLD_GUESS_LAST
+#define RG_COLD_GUESS_LAST 1
+#endif
 // cold start: rounds granted beyond cold_start_rounds while at most this many rows still move
 #ifndef RG_COLD_EXTEND_ROUNDS
 #define RG_COLD_EXTEND_ROUNDS 0
@@ -1100,6 +1104,10 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     if (!cold) {
 #pragma unroll
       for (int r = 0; r < 10; ++r) if (active_blk && lam[r] > 0.03 * s[r]) act |= 1u << r;
+    } else if (RG_COLD_GUESS_LAST && active_blk && t_blk >= H - RG_COLD_GUESS_LAST) {
+      // a force in the last step(s) of the horizon barely moves any tracked state, so the regulariser
+      // drives it to zero: fz >= fz_min is active there in practically every problem (bit 9)
+      act = 1u << 9;
     }
     bool polished = false, fact_valid = false;   // the factor in shared memory is the interior point's, if any
     unsigned act_fact = 0;
@@ -1193,7 +1201,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 #pragma unroll
       for (int d = 0; d < 3; ++d) up[d] = u0[d];
       double gr[3];
-      if (cold && round == 0) {
+      if (cold && round == 0 && RG_COLD_GUESS_LAST == 0) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) gr[d] = q[d];
       } else {
