@@ -250,6 +250,11 @@ extern "C" int rg_mpc_setup(const rg_mpc_params* p, void* workspace, size_t work
     rg_set_error("horizon table factorisation failed");
     return RG_ERR_SINGULAR;
   }
+  for (int jj = 0; jj < p->horizon; ++jj)
+    for (int kk = 0; kk <= jj; ++kk)
+      for (int t = 0; t < p->horizon; ++t)
+        h.eig_uu[(jj * (jj + 1) / 2 + kk) * p->horizon + t] = h.eig_u[jj * p->horizon + t] * h.eig_u[kk * p->horizon + t];
+
   {
     // env-independent tables: c2 and the inverse of the three linear channels of K,
     // K_lin,c = 2 dt^2 w_v,c c1 + 2 dt^4 w_p,c c2  =>  K_lin,c^-1 = U diag(1 / (k1 + gamma_t k2)) U^T

@@ -31,6 +31,8 @@ struct RgMpcDev {
   //   U^T c1 U = I,  U^T c2 U = diag(gamma);  eig_u is row-major [j][t].
   double eig_u[RG_MAX_HORIZON * RG_MAX_HORIZON];
   double eig_gamma[RG_MAX_HORIZON];
+  // eig_uu[(j(j+1)/2 + k) * h + t] = U[j][t] U[k][t], k <= j: the rank-h weights of K^-1's (j,k) time block
+  double eig_uu[RG_MAX_HORIZON * (RG_MAX_HORIZON + 1) / 2 * RG_MAX_HORIZON];
   // env-independent tables (host-computed, read through the L1/L2-cached uniform path):
   double c2tab[RG_MAX_HORIZON * RG_MAX_HORIZON];                        // c2(j,k), row-major h x h
   double kinv_lin[3][RG_MAX_HORIZON * (RG_MAX_HORIZON + 1) / 2];        // K^-1 of the x/y/z channels, packed

@@ -38,11 +38,13 @@ extern "C" int rg_debug_set_trace(double* dev_buf, int env) {
 #define RG_TRACE(slot, value) do { if (g_trace && env == g_trace_env && threadIdx.x == 0) g_trace[slot] = (value); } while (0)
 // phase timers: cycles accumulated in g_trace[900 + phase] by thread 0 of the traced env
 #define RG_TIC() long long rg_t0_ = clock64()
+#define RG_TRESET() rg_t0_ = clock64()
 #define RG_TOCL(phase, thr) do { if (g_trace && (int)blockIdx.x == g_trace_env && threadIdx.x == (thr)) g_trace[900 + (phase)] += (double)(clock64() - rg_t0_); rg_t0_ = clock64(); } while (0)
 #define RG_TOC(phase) do { if (g_trace && (int)blockIdx.x == g_trace_env && threadIdx.x == 0) g_trace[900 + (phase)] += (double)(clock64() - rg_t0_); rg_t0_ = clock64(); } while (0)
 #else
 #define RG_TRACE(slot, value) do { } while (0)
 #define RG_TIC() do { } while (0)
+#define RG_TRESET() do { } while (0)
 #define RG_TOC(phase) do { } while (0)
 #define RG_TOCL(phase, thr) do { } while (0)
 #endif
@@ -706,7 +708,18 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   const double big_u = (mu[0] + 1.0) * fzmax;
 
   // ---------------------------------------------------------------- per-env inputs
+  // every load is issued here, before anything depends on one of them: one DRAM latency, not four
   const unsigned contact_word = *reinterpret_cast<const unsigned*>(g_contacts + 4 * (size_t)env);
+  const float in_roll = g_rpy[3 * (size_t)env + 0], in_pitch = g_rpy[3 * (size_t)env + 1], in_yaw = g_rpy[3 * (size_t)env + 2];
+  float in_feet[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) in_feet[i] = g_feet[12 * (size_t)env + i];
+  const float in_com_h = g_com_height ? g_com_height[env] : 0.f;
+  const float in_w[3] = {g_rpy_rate[3 * (size_t)env + 0], g_rpy_rate[3 * (size_t)env + 1], g_rpy_rate[3 * (size_t)env + 2]};
+  const float in_v[3] = {g_com_vel[3 * (size_t)env + 0], g_com_vel[3 * (size_t)env + 1], g_com_vel[3 * (size_t)env + 2]};
+  const float in_cmd[3] = {g_cmd[3 * (size_t)env + 0], g_cmd[3 * (size_t)env + 1], g_cmd[3 * (size_t)env + 2]};
+  // stage the rank-h weights of K^-1 (host table) in the Psi buffer, which is free until the first factorisation
+  for (int i = tid; i < H * (H + 1) / 2 * H; i += blockDim.x) sm.psi[i] = ws->eig_uu[i];
   const bool stance_leg[4] = {(contact_word & 0xffu) != 0, (contact_word & 0xff00u) != 0,
                               (contact_word & 0xff0000u) != 0, (contact_word & 0xff000000u) != 0};
   const int n_stance = (int)stance_leg[0] + stance_leg[1] + stance_leg[2] + stance_leg[3];
@@ -719,8 +732,8 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     return;
   }
 
-  const double roll = g_rpy[3 * (size_t)env + 0], pitch = g_rpy[3 * (size_t)env + 1],
-               yaw = zero_yaw ? 0.0 : (double)g_rpy[3 * (size_t)env + 2];
+  RG_TIC();
+  const double roll = in_roll, pitch = in_pitch, yaw = zero_yaw ? 0.0 : (double)in_yaw;
   double sr, cr, sp, cp, sy, cy;
   sincos(roll, &sr, &cr);
   sincos(pitch, &sp, &cp);
@@ -729,6 +742,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   // ---------------------------------------------------------------- setup (thread 0..; tiny)
   if (tid == 0) sm.flag = 0;
 
+  RG_TOC(40);
   // T(rpy): angular velocity -> rpy rate;  K2_ang = 2 dt^4 T^T diag(w_rpy) T
   const double tm[9] = {cy / cp, sy / cp, 0.0, -sy, cy, 0.0, cy * sp / cp, sy * sp / cp, 1.0};
   const double dt2 = dt * dt, dt4 = dt2 * dt2;
@@ -753,13 +767,12 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     double fw[4][3];
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
-      const float* fp = g_feet + 12 * (size_t)env + 3 * l;
-      const double px = fp[0], py = fp[1], pz = fp[2];
+      const double px = in_feet[3 * l], py = in_feet[3 * l + 1], pz = in_feet[3 * l + 2];
 #pragma unroll
       for (int r = 0; r < 3; ++r) fw[l][r] = rf[3 * r] * px + rf[3 * r + 1] * py + rf[3 * r + 2] * pz;
       if (stance_leg[l]) zsum += fw[l][2];
     }
-    com_z = g_com_height ? (double)g_com_height[env] : fabs(zsum / n_stance);
+    com_z = g_com_height ? (double)in_com_h : fabs(zsum / n_stance);
     if (tid < 4) {
       const double rb[9] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
                             sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
@@ -798,6 +811,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     }
   }
   __syncthreads();
+  RG_TOC(41);
 
   // Q_t = (K1 + gamma_t K2)^-1 : 3x3 SPD angular block (packed xx,yy,zz,xz,yz,xy) + 3 scalars
   if (tid < H) {
@@ -815,57 +829,65 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     sm.nblk[tid][5] = c01 * id;                       // xy
   }
   __syncthreads();
+  RG_TOC(42);
 
-  // K^-1 = (U (x) I) blkdiag(Q_t) (U^T (x) I)
-  for (int idx = tid; idx < C::NKA; idx += blockDim.x) {
-    // invert tri(): a = row, b = col
-    int a = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
-    while (tri(a + 1, 0) <= idx) ++a;
-    while (tri(a, 0) > idx) --a;
-    const int b = idx - tri(a, 0);
-    const int j = a / 3, c = a % 3, k = b / 3, d = b % 3;
-    // packed index of the symmetric 3x3 (xx,yy,zz,xz,yz,xy)
-    const int lo = c < d ? c : d, hi = c < d ? d : c;
-    const int pk = (lo == hi) ? lo : (lo == 0 && hi == 2) ? 3 : (lo == 1 && hi == 2) ? 4 : 5;
+  // K^-1 = (U (x) I) blkdiag(Q_t) (U^T (x) I): one item per ((j,k) time block, packed 3x3 component),
+  // a rank-h sum with the host-tabulated weights U[j][t] U[k][t]
+  for (int it = tid; it < H * (H + 1) / 2 * 6; it += blockDim.x) {
+    const int p = it / 6, pk = it - 6 * p;
+    int j = (int)((sqrtf(8.f * p + 1.f) - 1.f) * 0.5f);
+    while (tri(j + 1, 0) <= p) ++j;
+    while (tri(j, 0) > p) --j;
+    const int k = p - tri(j, 0);
+    const double* uu = sm.psi + p * H;
     double v = 0.0;
-    for (int t = 0; t < H; ++t) v = fma(ws->eig_u[j * H + t] * ws->eig_u[k * H + t], sm.nblk[t][pk], v);
-    sm.kinv_ang[idx] = v;
+#pragma unroll
+    for (int t = 0; t < H; ++t) v = fma(uu[t], sm.nblk[t][pk], v);
+    // packed (xx,yy,zz,xz,yz,xy) -> (c,d), c <= d
+    const int c = pk < 3 ? pk : (pk == 4 ? 1 : 0), d = pk < 3 ? pk : (pk == 5 ? 1 : 2);
+    sm.kinv_ang[tri(3 * j + d, 3 * k + c)] = v;
+    if (j > k && c != d) sm.kinv_ang[tri(3 * j + c, 3 * k + d)] = v;
   }
-  // g~_j = 2 sum_{i>j} [ dt L_nu e_nu(i) + dt^2 (i-j-1/2) G6^T L_rho e_rho(i) ]   (thread per (j,c))
+  RG_TOC(43);
+  // g~_j = 2 sum_{i>j} [ dt L_nu e_nu(i) + dt^2 (i-j-1/2) G6^T L_rho e_rho(i) ]
+  // stage 1 (thread per horizon step i): the weighted errors of the free response against the reference
+  // trajectory, in sm.kvec (velocity part) and sm.avec (position part) -- both are free during the setup;
+  // stage 2 (thread per (j,c)): the two-term sums.
   {
-    const double wx = g_rpy_rate[3 * (size_t)env + 0], wy = g_rpy_rate[3 * (size_t)env + 1], wz = g_rpy_rate[3 * (size_t)env + 2];
-    const double vx = g_com_vel[3 * (size_t)env + 0], vy = g_com_vel[3 * (size_t)env + 1], vz = g_com_vel[3 * (size_t)env + 2];
-    const double dvx = g_cmd[3 * (size_t)env + 0], dvy = g_cmd[3 * (size_t)env + 1], dwz = g_cmd[3 * (size_t)env + 2];
+    const double wx = in_w[0], wy = in_w[1], wz = in_w[2];
+    const double vx = in_v[0], vy = in_v[1], vz = in_v[2];
+    const double dvx = in_cmd[0], dvy = in_cmd[1], dwz = in_cmd[2];
     const double grav = -ws->gravity;
-    // rpy rate at t0:  T w
-    const double rr0 = tm[0] * wx + tm[1] * wy + tm[2] * wz;
-    const double rr1 = tm[3] * wx + tm[4] * wy + tm[5] * wz;
-    const double rr2 = tm[6] * wx + tm[7] * wy + tm[8] * wz;
+    if (tid < H) {
+      const double ti = (tid + 1) * dt;
+      // rpy rate at t0:  T w
+      const double rr0 = tm[0] * wx + tm[1] * wy + tm[2] * wz;
+      const double rr1 = tm[3] * wx + tm[4] * wy + tm[5] * wz;
+      const double rr2 = tm[6] * wx + tm[7] * wy + tm[8] * wz;
+      const double er0 = roll + ti * rr0 - 0.0;
+      const double er1 = pitch + ti * rr1 - 0.0;
+      const double er2 = yaw + ti * rr2 - (yaw + ti * dwz);
+      const double ep[3] = {0.0 + ti * vx - ti * dvx, 0.0 + ti * vy - ti * dvy, com_z + ti * vz + 0.5 * ti * ti * grav - ws->height};
+      const double en[6] = {wx - 0.0, wy - 0.0, wz - dwz, vx - dvx, vy - dvy, vz + ti * grav - 0.0};
+      const double lr0 = ws->w_rho[0] * er0, lr1 = ws->w_rho[1] * er1, lr2 = ws->w_rho[2] * er2;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        sm.kvec[6 * tid + c] = ws->w_nu[c] * en[c];
+        sm.avec[6 * tid + c] = c < 3 ? tm[c] * lr0 + tm[3 + c] * lr1 + tm[6 + c] * lr2 : ws->w_rho[c] * ep[c - 3];   // (T^T L e)_c
+      }
+    }
+    __syncthreads();
     if (tid < N6) {
       const int j = tid / 6, c = tid % 6;
       double acc = 0.0;
-      for (int i = j + 1; i <= H; ++i) {
-        const double ti = i * dt;
-        // errors of the free response against the reference trajectory
-        const double er0 = roll + ti * rr0 - 0.0;
-        const double er1 = pitch + ti * rr1 - 0.0;
-        const double er2 = yaw + ti * rr2 - (yaw + ti * dwz);
-        const double ep0 = 0.0 + ti * vx - ti * dvx;
-        const double ep1 = 0.0 + ti * vy - ti * dvy;
-        const double ep2 = com_z + ti * vz + 0.5 * ti * ti * grav - ws->height;
-        const double en[6] = {wx - 0.0, wy - 0.0, wz - dwz, vx - dvx, vy - dvy, vz + ti * grav - 0.0};
-        const double lr0 = ws->w_rho[0] * er0, lr1 = ws->w_rho[1] * er1, lr2 = ws->w_rho[2] * er2;
-        double rho_term;
-        if (c < 3) rho_term = tm[c] * lr0 + tm[3 + c] * lr1 + tm[6 + c] * lr2;          // (T^T L e)_c
-        else rho_term = ws->w_rho[c] * (c == 3 ? ep0 : c == 4 ? ep1 : ep2);
-        acc += 2.0 * (dt * ws->w_nu[c] * en[c] + dt2 * (i - j - 0.5) * rho_term);
-      }
+      for (int i = j + 1; i <= H; ++i) acc += 2.0 * (dt * sm.kvec[6 * (i - 1) + c] + dt2 * (i - j - 0.5) * sm.avec[6 * (i - 1) + c]);
       sm.gt[tid] = acc;
     }
   }
   __syncthreads();
+  RG_TOC(44);
 
-  RG_TIC();
+  RG_TRESET();
 #ifdef RG_DEBUG_TRACE
   if (g_trace && (int)blockIdx.x == g_trace_env && threadIdx.x == 0) g_trace[900 + 8] += (double)(clock64() - rg_tstart_);
 #endif

@@ -65,12 +65,12 @@ def test_error_codes_and_messages(rg_lib):
     p = rg.default_mpc_params(19.4, (0.07, 0, 0, 0, 0.25, 0, 0, 0, 0.25), 0.42, 10)
     dummy = ctypes.create_string_buffer(16)
     assert rg_lib.rg_mpc_setup(ctypes.byref(p), dummy, 16, None) == -4        # RG_ERR_WORKSPACE (too small)
-    big = ctypes.create_string_buffer(32768)
+    big = ctypes.create_string_buffer(131072)
     p.weights[9] = 0.0; p.weights[3] = 0.0                                    # x channel unpenalised
-    assert rg_lib.rg_mpc_setup(ctypes.byref(p), big, 32768, None) == -3        # RG_ERR_SINGULAR
+    assert rg_lib.rg_mpc_setup(ctypes.byref(p), big, 131072, None) == -3        # RG_ERR_SINGULAR
     assert b"unpenalised" in rg_lib.rg_last_error()
     p.weights[9] = 0.2; p.friction_coeffs[2] = 0.0
-    assert rg_lib.rg_mpc_setup(ctypes.byref(p), big, 32768, None) == -1
+    assert rg_lib.rg_mpc_setup(ctypes.byref(p), big, 131072, None) == -1
     assert rg_lib.rg_mpc_build_solve(None, 4, *([None] * 10), None) == -1
     assert rg_lib.rg_gait_step(None, 4, None, None, None, None, None, None) == -1
     with pytest.raises(rg.RgCudaError) as err:

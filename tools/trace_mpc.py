@@ -15,7 +15,8 @@ from robot_gym import cuda as rg
 from robot_gym.model.robots.descriptions import GHOST, with_gait
 from robot_gym.util import synthetic
 
-PHASES = {8: "setup (inputs, tables, K^-1)", 0: "ipm: loop head", 1: "ipm: apply_p + residual", 2: "ipm: block parts",
+PHASES = {8: "setup (inputs, tables, K^-1)", 40: "  setup: input loads, sincos", 41: "  setup: K2, lever arms, I_w^-1", 42: "  setup: Q_t inverses",
+          43: "  setup: K^-1 angular (rank-h sums)", 44: "  setup: g~ + barrier", 0: "ipm: loop head", 1: "ipm: apply_p + residual", 2: "ipm: block parts",
           3: "ipm: factor_psi", 4: "ipm: rhs", 5: "ipm: woodbury", 6: "ipm: tail/step", 20: "as: basis + gap",
           12: "factor: n-blocks", 10: "factor: psi build", 11: "factor: cholesky", 21: "as: rhs", 22: "as: woodbury solve",
           23: "as: apply_p", 24: "as: verify + reduce", 7: "exit", 9: "TOTAL",
