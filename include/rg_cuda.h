@@ -206,6 +206,21 @@ int rg_swing_targets(const void* robot_workspace, int n_env, const int32_t* desi
 int rg_leg_ik(const void* robot_workspace, int n_env, const float* foot_local_position,
               const uint8_t* leg_mask, float* motor_angles, void* stream);
 
+/* State provider ("next" row f2 of SURVEY.md 8): the robot getters the controller stack pulls its inputs
+ * from, for a simulator that exposes raw rigid-body state instead of PyBullet queries.  Replaces
+ *   Robot.GetBaseRollPitchYaw          robot.py:79-86   (getEulerFromQuaternion of the base orientation)
+ *   Robot.GetBaseRollPitchYawRate      robot.py:205-213 -> TransformAngularVelocityToLocalFrame :185-203
+ *                                      (world angular velocity rotated by the inverse base orientation)
+ *   Robot.GetMotorAngles               robot.py:231-236 ((joint - MOTOR_OFFSET) * MOTOR_DIRECTION)
+ *   Robot.GetFootPositionsInBaseFrame  robot.py:389-397,367-383 (forward kinematics of the URDF chains
+ *                                      instead of four getLinkState round trips)
+ *   base_quat_xyzw [N,4] f32, base_ang_vel_world [N,3] f32 (may be NULL when base_rpy_rate is NULL),
+ *   joint_angles [N,12] f32 (raw URDF joint angles)  ->  base_rpy [N,3], base_rpy_rate [N,3],
+ *   motor_angles [N,12], foot_positions_base [N,4,3], all f32; any output may be NULL (skipped). */
+int rg_state_from_sim(const void* robot_workspace, int n_env, const float* base_quat_xyzw,
+                      const float* base_ang_vel_world, const float* joint_angles, float* base_rpy,
+                      float* base_rpy_rate, float* motor_angles, float* foot_positions_base, void* stream);
+
 /* Forward kinematics of the same chains (replaces Robot.GetFootPositionsInBaseFrame's
  * getLinkState round trips, robot.py:367-397, for a state provider without PyBullet). */
 int rg_leg_fk(const void* robot_workspace, int n_env, const float* motor_angles,

@@ -70,6 +70,36 @@ class LegChain:
         return (q + math.pi) % (2 * math.pi) - math.pi
 
 
+def quat_to_rpy(q_xyzw):
+    """``pybullet.getEulerFromQuaternion`` (called by Robot.GetBaseRollPitchYaw, robot.py:79-86): Bullet's
+    ZYX Euler extraction with its two gimbal-lock branches.  PyBullet is absent: restated from the published
+    btQuaternion::getEulerZYX algorithm (parity unpinned); pinned here by the euler -> quaternion -> euler
+    round trip and by agreement with the rotation matrix (tests/test_oracle_locomotion.py)."""
+    qx, qy, qz, qw = [float(v) for v in q_xyzw]
+    sqx, sqy, sqz, sqw = qx * qx, qy * qy, qz * qz, qw * qw
+    sarg = -2.0 * (qx * qz - qw * qy)
+    if sarg <= -0.99999:
+        return np.array([0.0, -0.5 * math.pi, 2.0 * math.atan2(qx, -qy)])
+    if sarg >= 0.99999:
+        return np.array([0.0, 0.5 * math.pi, 2.0 * math.atan2(-qx, qy)])
+    return np.array([math.atan2(2.0 * (qy * qz + qw * qx), sqw - sqx - sqy + sqz), math.asin(sarg),
+                     math.atan2(2.0 * (qx * qy + qw * qz), sqw + sqx - sqy - sqz)])
+
+
+def quat_to_matrix(q_xyzw):
+    """Rotation matrix of a Bullet (x, y, z, w) quaternion (getMatrixFromQuaternion)."""
+    x, y, z, w = [float(v) for v in q_xyzw]
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def angular_velocity_to_local_frame(angular_velocity_world, q_xyzw):
+    """Robot.TransformAngularVelocityToLocalFrame (robot.py:185-203): invertTransform + multiplyTransforms of a
+    pure rotation = R(q)^T w."""
+    return quat_to_matrix(q_xyzw).T @ np.asarray(angular_velocity_world, dtype=np.float64)
+
+
 class OracleRobot:
     """Holds one env's state and answers the getters the third-party stack calls (robot.py:71-264)."""
 
@@ -104,6 +134,16 @@ class OracleRobot:
     def fk_all(self, motor_angles):
         q = self.joint_angles(motor_angles)
         return np.stack([self._chains[l].fk(q[3 * l:3 * l + 3]) for l in range(4)])
+
+    def set_sim_state(self, base_orientation, base_velocity, base_angular_velocity_world, joint_angles, foot_contacts):
+        """State injection from RAW rigid-body state, through the same conversions Robot's getters apply to
+        PyBullet's answers (robot.py:79-86,185-213,231-236,367-397)."""
+        joint_angles = np.asarray(joint_angles, dtype=np.float64)
+        motor = (joint_angles - self._offset) * self._direction
+        self.set_state(base_velocity=base_velocity, base_orientation=base_orientation,
+                       base_rpy=quat_to_rpy(base_orientation),
+                       base_rpy_rate=angular_velocity_to_local_frame(base_angular_velocity_world, base_orientation),
+                       foot_positions=None, foot_contacts=foot_contacts, motor_angles=motor)
 
     # ---- robot.py callback surface
     def GetFootContacts(self):

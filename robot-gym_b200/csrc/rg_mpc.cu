@@ -68,7 +68,6 @@ struct Cfg {
 #endif
   static constexpr int NA = 3 * H;
   static constexpr int NKA = NA * (NA + 1) / 2;
-  static constexpr int NKL = H * (H + 1) / 2;
   static constexpr int RPL = (N6 + 31) / 32;   // Psi rows per lane in the triangular sweeps
   // resident CTAs per SM the register allocation is sized for (shared memory allows 9 / 2 at h = 10 / 20)
 #ifndef RG_MIN_BLOCKS_H10
@@ -113,16 +112,6 @@ __device__ __forceinline__ double2 ld2(const double* p) { return make_double2(p[
 #endif
 
 __device__ __forceinline__ double c1f(int h, int j, int k) { return (double)(h - (j > k ? j : k)); }
-
-__device__ __forceinline__ double c2f(int h, int j, int k) {
-  // sum_{i=m+1}^{h} (i - j - 1/2)(i - k - 1/2)
-  const int m = j > k ? j : k;
-  const double a = j + 0.5, b = k + 0.5;
-  const double cnt = h - m;
-  const double s1 = 0.5 * ((double)h * (h + 1) - (double)m * (m + 1));
-  const double s2 = ((double)h * (h + 1) * (2 * h + 1) - (double)m * (m + 1) * (2 * m + 1)) / 6.0;
-  return s2 - (a + b) * s1 + a * b * cnt;
-}
 
 // After the first solve of an active-set round the refinement pass is skipped when the projected
 // gradient is already below this (relative to the gradient scale): the error it leaves in the
@@ -1347,7 +1336,6 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
         g_mul(u, mu, c5);
 #pragma unroll
         for (int r = 0; r < 5; ++r) { s[r] = hv_up[r] - c5[r]; s[5 + r] = c5[r] - lo_b[r]; }
-#pragma unroll
       }
       continue;
     }

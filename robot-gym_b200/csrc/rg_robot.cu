@@ -282,6 +282,54 @@ __global__ void fk_kernel(const RgRobotDev* __restrict__ R, int n_env, const flo
   foot[3 * (size_t)idx] = (float)f.x; foot[3 * (size_t)idx + 1] = (float)f.y; foot[3 * (size_t)idx + 2] = (float)f.z;
 }
 
+// ---- state provider: raw rigid-body state -> the controller's inputs ---------------------------------
+// One thread per (env, leg): the leg's FK and motor angles; leg 0 also does the base quantities.
+__global__ void state_from_sim_kernel(const RgRobotDev* __restrict__ R, int n_env, const float* __restrict__ quat,
+                                      const float* __restrict__ ang_vel_world, const float* __restrict__ joint_angles,
+                                      float* __restrict__ rpy, float* __restrict__ rpy_rate, float* __restrict__ motor_angles,
+                                      float* __restrict__ foot) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 4 * n_env) return;
+  const int env = idx >> 2, leg = idx & 3;
+  double q[3];
+  for (int j = 0; j < 3; ++j) {
+    const int m = 3 * leg + j;
+    q[j] = joint_angles[12 * (size_t)env + m];
+    // Robot.GetMotorAngles (robot.py:231-236): (joint - MOTOR_OFFSET) * MOTOR_DIRECTION
+    if (motor_angles) motor_angles[12 * (size_t)env + m] = (float)((q[j] - R->motor_offset[m]) * R->motor_direction[m]);
+  }
+  if (foot) {
+    const V3 f = leg_fk(R->legs[leg], q, nullptr);
+    foot[3 * (size_t)idx] = (float)f.x; foot[3 * (size_t)idx + 1] = (float)f.y; foot[3 * (size_t)idx + 2] = (float)f.z;
+  }
+  if (leg != 0) return;
+  const double qx = quat[4 * (size_t)env + 0], qy = quat[4 * (size_t)env + 1], qz = quat[4 * (size_t)env + 2], qw = quat[4 * (size_t)env + 3];
+  if (rpy) {
+    // Bullet's getEulerFromQuaternion (ZYX convention, with its two gimbal-lock branches)
+    const double sqx = qx * qx, sqy = qy * qy, sqz = qz * qz, sqw = qw * qw;
+    const double sarg = -2.0 * (qx * qz - qw * qy);
+    double roll, pitch, yaw;
+    if (sarg <= -0.99999) { pitch = -0.5 * 3.14159265358979323846; roll = 0.0; yaw = 2.0 * atan2(qx, -qy); }
+    else if (sarg >= 0.99999) { pitch = 0.5 * 3.14159265358979323846; roll = 0.0; yaw = 2.0 * atan2(-qx, qy); }
+    else {
+      roll = atan2(2.0 * (qy * qz + qw * qx), sqw - sqx - sqy + sqz);
+      pitch = asin(sarg);
+      yaw = atan2(2.0 * (qx * qy + qw * qz), sqw + sqx - sqy - sqz);
+    }
+    rpy[3 * (size_t)env] = (float)roll; rpy[3 * (size_t)env + 1] = (float)pitch; rpy[3 * (size_t)env + 2] = (float)yaw;
+  }
+  if (rpy_rate) {
+    // Robot.TransformAngularVelocityToLocalFrame (robot.py:185-203): w_body = R(q)^T w_world
+    const double wx = ang_vel_world[3 * (size_t)env], wy = ang_vel_world[3 * (size_t)env + 1], wz = ang_vel_world[3 * (size_t)env + 2];
+    const double r00 = 1 - 2 * (qy * qy + qz * qz), r01 = 2 * (qx * qy - qz * qw), r02 = 2 * (qx * qz + qy * qw);
+    const double r10 = 2 * (qx * qy + qz * qw), r11 = 1 - 2 * (qx * qx + qz * qz), r12 = 2 * (qy * qz - qx * qw);
+    const double r20 = 2 * (qx * qz - qy * qw), r21 = 2 * (qy * qz + qx * qw), r22 = 1 - 2 * (qx * qx + qy * qy);
+    rpy_rate[3 * (size_t)env] = (float)(r00 * wx + r10 * wy + r20 * wz);
+    rpy_rate[3 * (size_t)env + 1] = (float)(r01 * wx + r11 * wy + r21 * wz);
+    rpy_rate[3 * (size_t)env + 2] = (float)(r02 * wx + r12 * wy + r22 * wz);
+  }
+}
+
 __device__ __forceinline__ void leg_torque(const RgRobotDev& R, int leg, const float* force, const float* angles, double* tau) {
   double q[3];
   for (int j = 0; j < 3; ++j) {
@@ -586,6 +634,18 @@ extern "C" int rg_leg_fk(const void* ws, int n_env, const float* angles, float* 
   fk_kernel<<<grid_for(4 * n_env, 256), 256, 0, (cudaStream_t)stream>>>((const RgRobotDev*)ws, n_env, angles, foot);
   rg_count_launch();
   return rg_check_cuda(cudaGetLastError(), "fk_kernel launch");
+}
+
+extern "C" int rg_state_from_sim(const void* ws, int n_env, const float* base_quat, const float* base_ang_vel_world,
+                                 const float* joint_angles, float* base_rpy, float* base_rpy_rate, float* motor_angles,
+                                 float* foot_positions_base, void* stream) {
+  if (n_env == 0) return RG_OK;   // empty batch: nothing to validate, nothing to launch
+  RG_REQUIRE(ws && base_quat && joint_angles && n_env >= 0 && (!base_rpy_rate || base_ang_vel_world) &&
+             (base_rpy || base_rpy_rate || motor_angles || foot_positions_base), "rg_state_from_sim");
+  state_from_sim_kernel<<<grid_for(4 * n_env, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const RgRobotDev*)ws, n_env, base_quat, base_ang_vel_world, joint_angles, base_rpy, base_rpy_rate, motor_angles, foot_positions_base);
+  rg_count_launch();
+  return rg_check_cuda(cudaGetLastError(), "state_from_sim_kernel launch");
 }
 
 extern "C" int rg_force_to_torque(const void* ws, int n_env, const float* forces, const float* angles, float* torques, void* stream) {

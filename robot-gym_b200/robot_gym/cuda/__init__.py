@@ -27,7 +27,7 @@ RG_STATUS_ACTIVE_SET_ONLY = 16
 EXPORTED_SYMBOLS = (
     "rg_mpc_default_params", "rg_workspace_bytes", "rg_mpc_setup", "rg_mpc_release", "rg_mpc_build_solve",
     "rg_robot_calibrate_ik", "rg_robot_workspace_bytes", "rg_robot_setup",
-    "rg_gait_step", "rg_com_velocity_update", "rg_swing_targets", "rg_leg_ik", "rg_leg_fk",
+    "rg_gait_step", "rg_com_velocity_update", "rg_swing_targets", "rg_leg_ik", "rg_leg_fk", "rg_state_from_sim",
     "rg_force_to_torque", "rg_pack_hybrid_action", "rg_control_step", "rg_hybrid_motor_torque",
     "rg_measure_fma_peak", "rg_launch_count", "rg_last_error", "rg_version",
 )
@@ -121,6 +121,7 @@ def load(build_if_missing: bool = False):
     lib.rg_swing_targets.argtypes = [c_void_p, c_int] + [c_void_p] * 10 + [c_void_p]
     lib.rg_leg_ik.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.rg_leg_fk.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    lib.rg_state_from_sim.argtypes = [c_void_p, c_int] + [c_void_p] * 7 + [c_void_p]
     lib.rg_force_to_torque.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.rg_pack_hybrid_action.argtypes = [c_void_p, c_int] + [c_void_p] * 5 + [c_void_p]
     lib.rg_control_step.argtypes = [c_void_p, c_void_p, c_int, POINTER(ControllerState), c_void_p]

@@ -13,6 +13,7 @@ from robot_gym import cuda as rg
 from robot_gym.controllers.mpc.batched_kinematics import BatchedKinematics, robot_params_from_description
 from robot_gym.controllers.mpc.batched_mpc_controller import BatchedMPCController
 from robot_gym.model.robots.descriptions import GHOST, K3LSO, with_gait
+from robot_gym.model.robots.sim_state_robot import SimStateRobotBatch
 from robot_gym.model.robots.synthetic_robot import SyntheticRobotBatch
 from robot_gym.util import synthetic
 
@@ -171,3 +172,77 @@ def test_controller_batched_subset_reset_and_stats(rg_lib, cuda_device):
     assert stats[0] == 256 and stats[4] == 256 and stats[6] == 0
     # most solves verify from the cold-start active-set iteration (0 interior-point iterations)
     assert 0 <= stats[1] / 256 <= 12 and 1 <= stats[3] / 256 <= 12
+
+
+@pytest.mark.parametrize("desc", [GHOST, K3LSO])
+def test_state_provider_from_raw_sim_state_matches_oracle(rg_lib, cuda_device, desc):
+    """rg_state_from_sim: rpy, body-frame angular velocity, motor angles and FK foot
+    positions from raw rigid-body state, against the oracle's restatement of the Robot getters -- including
+    envs at both gimbal-lock branches -- and a controller driven through the provider equals one driven
+    through the synthetic getter source fed with the oracle's conversions."""
+    n = 300
+    rng = np.random.default_rng(5)
+    rpy = np.column_stack([rng.uniform(-3.0, 3.0, n), rng.uniform(-1.5, 1.5, n), rng.uniform(-3.0, 3.0, n)])
+    rpy[0] = (0.0, np.pi / 2, 0.4); rpy[1] = (0.0, -np.pi / 2, -1.1); rpy[2] = 0.0
+    quat = synthetic.euler_to_quat_xyzw(rpy).astype(np.float32)
+    w_world = rng.uniform(-2, 2, (n, 3)).astype(np.float32)
+    v_world = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    oracle_robot = kinematics.OracleRobot(desc)
+    motor0 = np.asarray(desc.GetConstants().INIT_MOTOR_ANGLES, dtype=np.float64)
+    motor = motor0[None] + rng.uniform(-0.3, 0.3, (n, 12))
+    joints = np.stack([oracle_robot.joint_angles(m) for m in motor]).astype(np.float32)
+    contacts = (rng.uniform(0, 1, (n, 4)) < 0.6).astype(np.uint8)
+    robot = SimStateRobotBatch(desc, n, device=cuda_device)
+    t = torch.zeros(n, dtype=torch.float64, device=cuda_device)
+    robot.set_sim_state(t, _dev(quat, cuda_device), _dev(v_world, cuda_device), _dev(w_world, cuda_device),
+                        _dev(joints, cuda_device), _dev(contacts, cuda_device))
+    torch.cuda.synchronize()
+    g_rpy, g_rate = robot.GetBaseRollPitchYaw().cpu().numpy(), robot.GetBaseRollPitchYawRate().cpu().numpy()
+    g_motor, g_feet = robot.GetMotorAngles().cpu().numpy(), robot.GetFootPositionsInBaseFrame().cpu().numpy()
+    for i in range(n):
+        q64 = quat[i].astype(np.float64)
+        oracle_robot.set_sim_state(q64, v_world[i], w_world[i].astype(np.float64), joints[i].astype(np.float64), contacts[i])
+        ref_rpy = np.array(oracle_robot.GetBaseRollPitchYaw())
+        # compare rotations, not angles (float32 quaternions near +-pi wrap; gimbal envs fold roll into yaw)
+        assert np.abs(kinematics.quat_to_matrix(synthetic.euler_to_quat_xyzw(g_rpy[i:i + 1].astype(np.float64))[0])
+                      - kinematics.quat_to_matrix(q64 / np.linalg.norm(q64))).max() < 2e-5
+        if abs(abs(ref_rpy[1]) - np.pi / 2) > 1e-2:
+            d = np.abs(g_rpy[i] - ref_rpy); d = np.minimum(d, 2 * np.pi - d)
+            assert d.max() < 5e-6
+        assert np.abs(g_rate[i] - oracle_robot.GetBaseRollPitchYawRate()).max() < 2e-6
+        assert np.abs(g_motor[i] - oracle_robot.GetMotorAngles()).max() < 1e-6
+        assert np.abs(g_feet[i] - oracle_robot.GetFootPositionsInBaseFrame()).max() < 1e-6
+    assert g_rpy[0, 0] == 0.0 and abs(g_rpy[0, 1] - np.pi / 2) < 1e-6          # gimbal branches taken
+    assert g_rpy[1, 0] == 0.0 and abs(g_rpy[1, 1] + np.pi / 2) < 1e-6
+    # NULL outputs are skipped, NULL inputs rejected
+    lib = rg.load()
+    assert lib.rg_state_from_sim(robot._ws.ptr, n, quat.ctypes.data, None, joints.ctypes.data, None, None, None, None, None) == -1
+    only_feet = torch.zeros((n, 12), dtype=torch.float32, device=cuda_device)
+    rg.check(lib.rg_state_from_sim(robot._ws.ptr, n, rg._ptr(_dev(quat, cuda_device), torch.float32, (4,)), None,
+                                   rg._ptr(_dev(joints, cuda_device), torch.float32, (12,)), None, None, None,
+                                   rg._ptr(only_feet, torch.float32, (12,)), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(only_feet.cpu().numpy(), g_feet.reshape(n, 12))
+    assert lib.rg_state_from_sim(robot._ws.ptr, 0, None, None, None, None, None, None, None, None) == 0   # empty batch
+
+    # the provider drives the controller exactly like the synthetic getter source with the same derived state
+    small = n if n < 64 else 64
+    sl = slice(0, small)
+    states = synthetic.SyntheticStates(
+        time_since_reset=np.zeros(small), foot_contacts=contacts[sl], base_velocity_world=v_world[sl],
+        base_orientation_xyzw=quat[sl], base_rpy=g_rpy[sl], base_rpy_rate=g_rate[sl],
+        foot_positions_base=g_feet[sl].reshape(small, 12), motor_angles=g_motor[sl],
+        com_velocity_body=np.zeros((small, 3), np.float32), planned_contacts=contacts[sl], command=np.zeros((small, 3), np.float32),
+        com_height=np.zeros(small, np.float32))
+    ref_robot = SyntheticRobotBatch(desc, states, device=cuda_device)
+    sim_robot = SimStateRobotBatch(desc, small, device=cuda_device)
+    tt = torch.full((small,), 0.05, dtype=torch.float64, device=cuda_device)
+    sim_robot.set_sim_state(tt, _dev(quat[sl], cuda_device), _dev(v_world[sl], cuda_device), _dev(w_world[sl], cuda_device),
+                            _dev(joints[sl], cuda_device), _dev(contacts[sl], cuda_device))
+    ref_robot.time_since_reset = tt
+    a_ref = BatchedMPCController(ref_robot, ref_robot.GetTimeSinceReset)
+    a_sim = BatchedMPCController(sim_robot, sim_robot.GetTimeSinceReset)
+    for c in (a_ref, a_sim):
+        c.update_controller_params(torch.tensor([[0.2, 0.0, 0.1]] * small))
+    out_ref, out_sim = a_ref.get_action().cpu().numpy(), a_sim.get_action().cpu().numpy()
+    assert np.array_equal(out_ref, out_sim)

@@ -210,3 +210,42 @@ def test_control_step_oracle_matches_frozen_golden(golden_dir):
         np.testing.assert_array_equal(np.asarray(ctl.gait_generator.normalized_phase).view(np.int64),
                                       g["normalized_phase"][k, e].view(np.int64))     # bit-exact
         np.testing.assert_allclose(action, g["actions"][k, e], rtol=1e-6, atol=1e-6)
+
+
+def test_quaternion_conversions_round_trip_and_gimbal_branches():
+    """State-provider conversions (robot.py:79-86,185-203): euler -> quaternion -> euler is the identity
+    away from gimbal lock, the Euler angles reproduce the rotation matrix, and R(q)^T w is the inverse
+    rotation of w."""
+    rng = np.random.default_rng(11)
+    rpy = np.column_stack([rng.uniform(-3.1, 3.1, 200), rng.uniform(-1.5, 1.5, 200), rng.uniform(-3.1, 3.1, 200)])
+    quat = synthetic.euler_to_quat_xyzw(rpy)
+    for e, q in zip(rpy, quat):
+        back = kinematics.quat_to_rpy(q)
+        assert np.abs(back - e).max() < 1e-9
+        r, p, y = back
+        rz = np.array([[math.cos(y), -math.sin(y), 0], [math.sin(y), math.cos(y), 0], [0, 0, 1]])
+        ry = np.array([[math.cos(p), 0, math.sin(p)], [0, 1, 0], [-math.sin(p), 0, math.cos(p)]])
+        rx = np.array([[1, 0, 0], [0, math.cos(r), -math.sin(r)], [0, math.sin(r), math.cos(r)]])
+        assert np.abs(rz @ ry @ rx - kinematics.quat_to_matrix(q)).max() < 1e-12
+        w = rng.uniform(-2, 2, 3)
+        local = kinematics.angular_velocity_to_local_frame(w, q)
+        assert np.abs(kinematics.quat_to_matrix(q) @ local - w).max() < 1e-12
+    # gimbal lock: pitch = +-90 deg keeps roll = 0 and folds everything into yaw
+    for sign in (1.0, -1.0):
+        q = synthetic.euler_to_quat_xyzw(np.array([[0.0, sign * math.pi / 2, 0.7]]))[0]
+        r, p, y = kinematics.quat_to_rpy(q)
+        assert r == 0.0 and abs(p - sign * math.pi / 2) < 1e-12 and abs(y - 0.7) < 1e-6
+    assert np.all(kinematics.quat_to_rpy([0, 0, 0, 1]) == 0.0)
+
+
+def test_oracle_robot_sim_state_injection_matches_direct_state():
+    robot = kinematics.OracleRobot(GHOST)
+    motor = np.asarray(GHOST.GetConstants().INIT_MOTOR_ANGLES, dtype=np.float64) + 0.05
+    joints = robot.joint_angles(motor)
+    q = synthetic.euler_to_quat_xyzw(np.array([[0.1, -0.2, 0.3]]))[0]
+    robot.set_sim_state(q, (0.3, 0.0, -0.1), (0.2, -0.4, 0.5), joints, (1, 0, 0, 1))
+    assert np.abs(np.array(robot.GetBaseRollPitchYaw()) - [0.1, -0.2, 0.3]).max() < 1e-12
+    assert np.abs(robot.GetMotorAngles() - motor).max() < 1e-12
+    assert np.abs(robot.GetFootPositionsInBaseFrame() - robot.fk_all(motor)).max() == 0.0
+    assert np.abs(kinematics.quat_to_matrix(q) @ robot.GetBaseRollPitchYawRate() - [0.2, -0.4, 0.5]).max() < 1e-12
+    assert robot.GetFootContacts() == [True, False, False, True]
