@@ -84,7 +84,8 @@ typedef struct rg_mpc_params {
   /* solver controls (not in the reference: OSQP eps/polish have no equivalent here) */
   double ipm_tol;              /* relative residual at which the interior point hands over (1e-6) */
   int32_t max_ipm_iters;       /* hard cap (40) */
-  int32_t max_polish_rounds;   /* 0 disables the active-set polish; rounds per attempt (3) */
+  int32_t max_polish_rounds;   /* rounds per attempt (3); 0 disables the verified active-set rounds:
+                                  the interior point alone leaves ~1e-3 relative in the alpha-directions */
   int32_t cold_start_rounds;   /* active-set rounds tried from the unconstrained minimiser BEFORE the
                                   interior point (5; it also stops as soon as the number of
                                   rows that move stops shrinking); 0 = always run the interior point first */

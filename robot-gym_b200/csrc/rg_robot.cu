@@ -28,7 +28,8 @@ __host__ __device__ inline V3 mat_tmul(const double* m, V3 v) {  // M^T v
 }
 // Rodrigues rotation of v about the unit axis a by angle q
 __host__ __device__ inline V3 rot_axis(V3 a, double q, V3 v) {
-  const double c = cos(q), s = sin(q);
+  double s, c;
+  sincos(q, &s, &c);
   return add(add(mul(c, v), mul(s, cross(a, v))), mul((1.0 - c) * dot(a, v), a));
 }
 __host__ __device__ inline double wrap_pi(double a) {
