@@ -140,7 +140,7 @@ __device__ __forceinline__ double c1f(int h, int j, int k) { return (double)(h -
 #define RG_IPM_WARM 0.99
 #endif
 #ifndef RG_SKIP_REFINE_TOL
-#define RG_SKIP_REFINE_TOL 1e-11
+#define RG_SKIP_REFINE_TOL 1e-10
 #endif
 
 // ---- block-wide reductions (all threads call; result valid in all threads) -------------------
