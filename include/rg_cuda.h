@@ -130,6 +130,20 @@ int rg_mpc_build_solve(const void* workspace, int n_env,
                        float* contact_forces, float* horizon_forces, int32_t* solve_info,
                        void* stream);
 
+/* Same solve, warm-started: `active_set_io` [N, 4*horizon] u16 holds, per (step, leg) block, the bit mask of
+ * the rows the previous solve of the same env verified active (bits 0-4: upper bounds of the five pyramid
+ * rows, bits 5-9: lower bounds) or RG_ACTIVE_SET_UNKNOWN.  It seeds the active-set iteration and is
+ * overwritten with this solve's verified set (UNKNOWN for swing blocks and unverified solves).  Consecutive
+ * control steps of one env see almost the same QP, so the seed usually verifies in a single round.  The
+ * result is the same unique optimum whatever the seed; initialise the buffer to 0xFF bytes.
+ * (No counterpart in the reference: OSQP is re-created cold on every compute_contact_forces call.) */
+#define RG_ACTIVE_SET_UNKNOWN 0xFFFFu
+int rg_mpc_build_solve_warm(const void* workspace, int n_env, const float* com_velocity_body,
+                            const float* base_rpy, const float* base_rpy_rate,
+                            const uint8_t* foot_contact_state, const float* foot_positions_base,
+                            const float* command, const float* com_height, float* contact_forces,
+                            float* horizon_forces, int32_t* solve_info, uint16_t* active_set_io, void* stream);
+
 /* ---- robot model: leg chains + gait + gains ------------------------------------------------
  * Replaces the per-robot python constants the third-party stack reads through the robot
  * callbacks (robot.py:88-92,169-170; ghost/ctrl_constants.py:13,28-41;
@@ -262,6 +276,7 @@ typedef struct rg_controller_state {
   float* phase_switch_foot_local_position; /* [N,12] */
   float* swing_joint_angles;             /* [N,12] */
   uint8_t* swing_joint_valid;            /* [N,4]  */
+  uint16_t* mpc_active_set;              /* [N,4*horizon] warm start of the stance QP (rg_mpc_build_solve_warm) or NULL */
   /* outputs */
   int32_t* desired_leg_state; int32_t* leg_state; double* normalized_phase;   /* [N,4] each */
   uint8_t* mpc_contact_state;            /* [N,4]  planned-stance flags handed to the MPC */

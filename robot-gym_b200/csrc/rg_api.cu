@@ -292,6 +292,16 @@ extern "C" int rg_mpc_build_solve(const void* workspace, int n_env, const float*
                                   const uint8_t* foot_contact_state, const float* foot_positions_base,
                                   const float* command, const float* com_height, float* contact_forces,
                                   float* horizon_forces, int32_t* solve_info, void* stream) {
+  return rg_mpc_build_solve_warm(workspace, n_env, com_velocity_body, base_rpy, base_rpy_rate, foot_contact_state,
+                                 foot_positions_base, command, com_height, contact_forces, horizon_forces, solve_info,
+                                 nullptr, stream);
+}
+
+extern "C" int rg_mpc_build_solve_warm(const void* workspace, int n_env, const float* com_velocity_body,
+                                       const float* base_rpy, const float* base_rpy_rate,
+                                       const uint8_t* foot_contact_state, const float* foot_positions_base,
+                                       const float* command, const float* com_height, float* contact_forces,
+                                       float* horizon_forces, int32_t* solve_info, uint16_t* active_set_io, void* stream) {
   if (n_env == 0) return RG_OK;   // empty batch: nothing to validate, nothing to launch
   if (!workspace || !com_velocity_body || !base_rpy || !base_rpy_rate || !foot_contact_state ||
       !foot_positions_base || !command || !contact_forces) {
@@ -304,7 +314,7 @@ extern "C" int rg_mpc_build_solve(const void* workspace, int n_env, const float*
   if (rc != RG_OK) return rc;
   return rg_launch_mpc((const RgMpcDev*)workspace, horizon, n_env, com_velocity_body, base_rpy, base_rpy_rate,
                        foot_contact_state, foot_positions_base, command, com_height, 0, contact_forces, horizon_forces,
-                       solve_info, (cudaStream_t)stream);
+                       solve_info, active_set_io, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------

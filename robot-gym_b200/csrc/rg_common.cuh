@@ -83,7 +83,7 @@ void rg_count_launch();
 struct rg_controller_state;
 int rg_launch_mpc(const RgMpcDev* ws, int horizon, int n_env, const float* com_vel, const float* rpy,
                   const float* rpy_rate, const uint8_t* contacts, const float* feet, const float* command,
-                  const float* com_height, int zero_yaw, float* forces, float* horizon_forces, int32_t* info,
+                  const float* com_height, int zero_yaw, float* forces, float* horizon_forces, int32_t* info, uint16_t* active_set,
                   cudaStream_t stream);
 // horizon stored in a prepared MPC workspace (host-side registry, falls back to a header read)
 int rg_mpc_workspace_horizon(const void* workspace, int* horizon);

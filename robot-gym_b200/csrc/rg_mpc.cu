@@ -665,7 +665,8 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
                  const float* __restrict__ g_rpy_rate, const uint8_t* __restrict__ g_contacts,
                  const float* __restrict__ g_feet, const float* __restrict__ g_cmd,
                  const float* __restrict__ g_com_height, int zero_yaw,
-                 float* __restrict__ g_forces, float* __restrict__ g_hforces, int32_t* __restrict__ g_info) {
+                 float* __restrict__ g_forces, float* __restrict__ g_hforces, int32_t* __restrict__ g_info,
+                 uint16_t* __restrict__ g_active) {
   using C = Cfg<H>;
   constexpr int N6 = C::N6;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -707,6 +708,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   const float in_w[3] = {g_rpy_rate[3 * (size_t)env + 0], g_rpy_rate[3 * (size_t)env + 1], g_rpy_rate[3 * (size_t)env + 2]};
   const float in_v[3] = {g_com_vel[3 * (size_t)env + 0], g_com_vel[3 * (size_t)env + 1], g_com_vel[3 * (size_t)env + 2]};
   const float in_cmd[3] = {g_cmd[3 * (size_t)env + 0], g_cmd[3 * (size_t)env + 1], g_cmd[3 * (size_t)env + 2]};
+  const unsigned warm_act = (g_active && is_blk) ? (unsigned)g_active[(size_t)env * C::NB + tid] : (unsigned)RG_ACTIVE_SET_UNKNOWN;
   // stage the rank-h weights of K^-1 (host table) in the Psi buffer, which is free until the first factorisation
   for (int i = tid; i < H * (H + 1) / 2 * H; i += blockDim.x) sm.psi[i] = ws->eig_uu[i];
   const bool stance_leg[4] = {(contact_word & 0xffu) != 0, (contact_word & 0xff00u) != 0,
@@ -718,6 +720,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     for (int i = tid; i < 12; i += blockDim.x) g_forces[12 * (size_t)env + i] = 0.f;
     if (g_hforces) for (int i = tid; i < 12 * H; i += blockDim.x) g_hforces[12 * H * (size_t)env + i] = 0.f;
     if (g_info && tid < 4) g_info[4 * (size_t)env + tid] = tid == RG_INFO_STATUS ? (RG_STATUS_NO_STANCE | RG_STATUS_POLISHED) : 0;
+    if (g_active && is_blk) g_active[(size_t)env * C::NB + tid] = RG_ACTIVE_SET_UNKNOWN;
     return;
   }
 
@@ -932,6 +935,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   const int max_polish = ws->max_polish_rounds;
   double tol = ws->ipm_tol;
   int iters = 0, polish_rounds = 0, status = 0, n_active_out = 0;
+  unsigned act_out = RG_ACTIVE_SET_UNKNOWN;
   double u_out[3] = {u[0], u[1], u[2]};
 
   // Escalation ladder: interior point to `tol`, then the active-set polish; if the polish does not
@@ -1115,6 +1119,10 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     if (!cold) {
 #pragma unroll
       for (int r = 0; r < 10; ++r) if (active_blk && lam[r] > 0.03 * s[r]) act |= 1u << r;
+    } else if (warm_act != RG_ACTIVE_SET_UNKNOWN) {
+      // warm start: the verified active set of this block from the previous solve of the same env
+      // (consecutive control steps see almost the same problem); wrong guesses are repaired by the rounds
+      act = active_blk ? warm_act : 0u;
     } else if (RG_COLD_GUESS_LAST && active_blk && t_blk >= H - RG_COLD_GUESS_LAST) {
       // a force in the last step(s) of the horizon barely moves any tracked state, so the regulariser
       // drives it to zero: fz >= fz_min is active there in practically every problem (bit 9)
@@ -1303,6 +1311,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       act = act_new;
     }
     if (polished) {
+      act_out = act;
       status |= cold ? (RG_STATUS_POLISHED | RG_STATUS_ACTIVE_SET_ONLY) : RG_STATUS_POLISHED;
 #pragma unroll
       for (int d = 0; d < 3; ++d) u_out[d] = up[d];
@@ -1369,6 +1378,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       o[0] = fx; o[1] = fy; o[2] = fz;
     }
   }
+  if (g_active && is_blk) g_active[(size_t)env * C::NB + tid] = (uint16_t)((done && active_blk) ? act_out : RG_ACTIVE_SET_UNKNOWN);
   if (g_info && tid == 0) {
     int32_t* o = g_info + 4 * (size_t)env;
     o[RG_INFO_IPM_ITERS] = iters;
@@ -1381,7 +1391,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 template <int H>
 int launch_h(const RgMpcDev* ws, int n_env, const float* com_vel, const float* rpy, const float* rpy_rate,
              const uint8_t* contacts, const float* feet, const float* command, const float* com_height,
-             int zero_yaw, float* forces, float* horizon_forces, int32_t* info, cudaStream_t stream) {
+             int zero_yaw, float* forces, float* horizon_forces, int32_t* info, uint16_t* active_set, cudaStream_t stream) {
   const size_t smem = sizeof(Smem<H>);
   static bool attr_set = false;
   if (!attr_set) {
@@ -1401,7 +1411,7 @@ int launch_h(const RgMpcDev* ws, int n_env, const float* com_vel, const float* r
     attr_set = true;
   }
   mpc_solve_kernel<H><<<n_env, Cfg<H>::NT, smem, stream>>>(ws, n_env, com_vel, rpy, rpy_rate, contacts, feet, command,
-                                                            com_height, zero_yaw, forces, horizon_forces, info);
+                                                            com_height, zero_yaw, forces, horizon_forces, info, active_set);
   rg_count_launch();
   return rg_check_cuda(cudaGetLastError(), "mpc_solve_kernel launch");
 }
@@ -1455,11 +1465,11 @@ extern "C" int rg_debug_chol_solve(int horizon, const double* a_dense, const dou
 int rg_launch_mpc(const RgMpcDev* ws, int horizon, int n_env, const float* com_vel, const float* rpy,
                   const float* rpy_rate, const uint8_t* contacts, const float* feet, const float* command,
                   const float* com_height, int zero_yaw, float* forces, float* horizon_forces, int32_t* info,
-                  cudaStream_t stream) {
+                  uint16_t* active_set, cudaStream_t stream) {
   switch (horizon) {
-    case 5: return launch_h<5>(ws, n_env, com_vel, rpy, rpy_rate, contacts, feet, command, com_height, zero_yaw, forces, horizon_forces, info, stream);
-    case 10: return launch_h<10>(ws, n_env, com_vel, rpy, rpy_rate, contacts, feet, command, com_height, zero_yaw, forces, horizon_forces, info, stream);
-    case 20: return launch_h<20>(ws, n_env, com_vel, rpy, rpy_rate, contacts, feet, command, com_height, zero_yaw, forces, horizon_forces, info, stream);
+    case 5: return launch_h<5>(ws, n_env, com_vel, rpy, rpy_rate, contacts, feet, command, com_height, zero_yaw, forces, horizon_forces, info, active_set, stream);
+    case 10: return launch_h<10>(ws, n_env, com_vel, rpy, rpy_rate, contacts, feet, command, com_height, zero_yaw, forces, horizon_forces, info, active_set, stream);
+    case 20: return launch_h<20>(ws, n_env, com_vel, rpy, rpy_rate, contacts, feet, command, com_height, zero_yaw, forces, horizon_forces, info, active_set, stream);
     default:
       rg_set_error("unsupported horizon %d (kernels are built for 5, 10, 20)", horizon);
       return RG_ERR_UNSUPPORTED;

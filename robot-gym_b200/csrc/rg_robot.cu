@@ -695,7 +695,7 @@ extern "C" int rg_control_step(const void* mpc_ws, const void* robot_ws, int n_e
   // TorqueStanceLegController.get_action zeroes the yaw before the solve ("yaw aligned world frame")
   rc = rg_launch_mpc((const RgMpcDev*)mpc_ws, horizon, n_env, s->com_velocity_body, s->base_rpy, s->base_rpy_rate,
                      s->mpc_contact_state, s->foot_positions_base, s->command, nullptr, /*zero_yaw=*/1,
-                     s->contact_forces, nullptr, s->solve_info, st);
+                     s->contact_forces, nullptr, s->solve_info, s->mpc_active_set, st);
   if (rc != RG_OK) return rc;
   step_epilogue_kernel<<<grid_for(4 * n_env, 256), 256, 0, st>>>((const RgRobotDev*)robot_ws, n_env, *s);
   rg_count_launch();

@@ -62,10 +62,13 @@ class BatchedMPCController(Controller):
 
     MOTOR_CONTROL_MODE = MOTOR_CONTROL_HYBRID      # mpc_controller.py:16
 
-    def __init__(self, robot, get_time_since_reset, horizon=10, mpc_overrides=None, squeeze_single=True):
+    def __init__(self, robot, get_time_since_reset, horizon=10, mpc_overrides=None, squeeze_single=True,
+                 warm_start=True):
         """``robot``: batched state provider with the getter names of robot.py (see
         ``SyntheticRobotBatch``); ``get_time_since_reset``: callable returning a float or an
-        ``[N]`` float64 tensor (Simulation.GetTimeSinceReset, core/simulation.py:141-142)."""
+        ``[N]`` float64 tensor (Simulation.GetTimeSinceReset, core/simulation.py:141-142).
+        ``warm_start``: seed each stance QP with the active set the same env verified one control step
+        earlier (``rg_mpc_build_solve_warm``); the optimum is unique, so the forces do not depend on it."""
         super().__init__(robot, get_time_since_reset)
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedMPCController needs a CUDA device (no CPU fallback)")
@@ -116,6 +119,7 @@ class BatchedMPCController(Controller):
         self.contact_forces = z((n, 12), f32)
         self.motor_torques = z((n, 12), f32)
         self.solve_info = z((n, 4), i32)
+        self.mpc_active_set = rg.new_active_set(n, self.horizon, dev) if warm_start else None
         self.action = z((n, 60), f32)
         self.reset_time = z((n,), f64)
         self.time_since_reset = z((n,), f64)
@@ -183,6 +187,8 @@ class BatchedMPCController(Controller):
         feet = self._robot.GetFootPositionsInBaseFrame().reshape(self.num_envs, 12)
         self.phase_switch_foot_local_position[sel] = feet[sel].to(torch.float32)
         self.swing_joint_valid[sel] = 0
+        if self.mpc_active_set is not None:
+            self.mpc_active_set[sel] = -1   # RG_ACTIVE_SET_UNKNOWN
         init_state = torch.tensor([int(s) for s in self._constants.INIT_LEG_STATE], dtype=torch.int32, device=self.device)
         self.desired_leg_state[sel] = init_state
         self.leg_state[sel] = init_state
@@ -223,6 +229,7 @@ class BatchedMPCController(Controller):
         st.phase_switch_foot_local_position = P(self.phase_switch_foot_local_position, f32)
         st.swing_joint_angles = P(self.swing_joint_angles, f32)
         st.swing_joint_valid = P(self.swing_joint_valid, u8)
+        st.mpc_active_set = P(self.mpc_active_set, torch.int16, allow_none=True)
         st.desired_leg_state = P(self.desired_leg_state, i32)
         st.leg_state = P(self.leg_state, i32)
         st.normalized_phase = P(self.normalized_phase, f64)

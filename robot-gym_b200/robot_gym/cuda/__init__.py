@@ -26,6 +26,7 @@ RG_STATUS_ACTIVE_SET_ONLY = 16
 # every symbol include/rg_cuda.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
     "rg_mpc_default_params", "rg_workspace_bytes", "rg_mpc_setup", "rg_mpc_release", "rg_mpc_build_solve",
+    "rg_mpc_build_solve_warm",
     "rg_robot_calibrate_ik", "rg_robot_workspace_bytes", "rg_robot_setup",
     "rg_gait_step", "rg_com_velocity_update", "rg_swing_targets", "rg_leg_ik", "rg_leg_fk", "rg_state_from_sim",
     "rg_force_to_torque", "rg_pack_hybrid_action", "rg_control_step", "rg_hybrid_motor_torque",
@@ -74,6 +75,7 @@ class ControllerState(Structure):
         "base_rpy_rate", "foot_positions_base", "motor_angles", "command",
         "vel_window", "vel_window_sum", "vel_window_corr", "vel_window_count", "vel_window_head",
         "last_leg_state", "phase_switch_foot_local_position", "swing_joint_angles", "swing_joint_valid",
+        "mpc_active_set",
         "desired_leg_state", "leg_state", "normalized_phase", "mpc_contact_state", "swing_foot_target",
         "com_velocity_body", "contact_forces", "motor_torques", "solve_info", "action")]
 
@@ -113,6 +115,7 @@ def load(build_if_missing: bool = False):
     lib.rg_mpc_setup.argtypes = [POINTER(MpcParams), c_void_p, c_size_t, c_void_p]
     lib.rg_mpc_release.argtypes = [c_void_p]
     lib.rg_mpc_build_solve.argtypes = [c_void_p, c_int] + [c_void_p] * 10 + [c_void_p]
+    lib.rg_mpc_build_solve_warm.argtypes = [c_void_p, c_int] + [c_void_p] * 11 + [c_void_p]
     lib.rg_robot_calibrate_ik.argtypes = [POINTER(RobotParams), POINTER(c_double)]
     lib.rg_robot_workspace_bytes.argtypes = [POINTER(c_size_t)]
     lib.rg_robot_setup.argtypes = [POINTER(RobotParams), c_void_p, c_size_t, c_void_p]
@@ -234,8 +237,10 @@ def calibrate_ik(params: RobotParams, reference_motor_angles) -> None:
 
 def mpc_build_solve(ws: MpcWorkspace, com_velocity_body, base_rpy, base_rpy_rate, foot_contact_state,
                     foot_positions_base, command, com_height=None, contact_forces=None,
-                    horizon_forces=None, solve_info=None, want_horizon=False, want_info=True):
-    """``rg_mpc_build_solve`` on the current stream.  Returns (contact_forces, horizon_forces, solve_info)."""
+                    horizon_forces=None, solve_info=None, want_horizon=False, want_info=True, active_set=None):
+    """``rg_mpc_build_solve`` (``rg_mpc_build_solve_warm`` when ``active_set`` -- an ``[N, 4*horizon]`` int16 tensor
+    initialised to -1, see ``new_active_set`` -- is given) on the current stream.
+    Returns (contact_forces, horizon_forces, solve_info)."""
     import torch
     n = base_rpy.shape[0]
     dev = base_rpy.device
@@ -246,12 +251,20 @@ def mpc_build_solve(ws: MpcWorkspace, com_velocity_body, base_rpy, base_rpy_rate
     if solve_info is None and want_info:
         solve_info = torch.empty((n, 4), dtype=torch.int32, device=dev)
     hf = None if horizon_forces is None else _ptr(horizon_forces.view(n, ws.horizon * 12), torch.float32, (ws.horizon * 12,))
-    check(load().rg_mpc_build_solve(
+    check(load().rg_mpc_build_solve_warm(
         ws.ptr, n,
         _ptr(com_velocity_body, torch.float32, (3,)), _ptr(base_rpy, torch.float32, (3,)),
         _ptr(base_rpy_rate, torch.float32, (3,)), _ptr(foot_contact_state, torch.uint8, (4,)),
         _ptr(foot_positions_base.view(n, 12), torch.float32, (12,)), _ptr(command, torch.float32, (3,)),
         _ptr(com_height, torch.float32, (), allow_none=True),
         _ptr(contact_forces, torch.float32, (12,)), hf,
-        _ptr(solve_info, torch.int32, (4,), allow_none=True), current_stream_ptr()))
+        _ptr(solve_info, torch.int32, (4,), allow_none=True),
+        _ptr(active_set, torch.int16, (4 * ws.horizon,), allow_none=True), current_stream_ptr()))
     return contact_forces, horizon_forces, solve_info
+
+
+def new_active_set(n_env, horizon, device="cuda"):
+    """Warm-start buffer of ``rg_mpc_build_solve_warm``: ``[N, 4*horizon]`` 16-bit words, all RG_ACTIVE_SET_UNKNOWN
+    (torch has no uint16 arithmetic: int16 -1 is the same bit pattern 0xFFFF)."""
+    import torch
+    return torch.full((n_env, 4 * horizon), -1, dtype=torch.int16, device=device)

@@ -246,3 +246,37 @@ def test_state_provider_from_raw_sim_state_matches_oracle(rg_lib, cuda_device, d
         c.update_controller_params(torch.tensor([[0.2, 0.0, 0.1]] * small))
     out_ref, out_sim = a_ref.get_action().cpu().numpy(), a_sim.get_action().cpu().numpy()
     assert np.array_equal(out_ref, out_sim)
+
+
+def test_controller_warm_start_matches_cold_controller_over_a_rollout(rg_lib, cuda_device):
+    """BatchedMPCController(warm_start=True) (the default) and warm_start=False produce the same actions over a
+    rollout with advancing gait and drifting state; the warm one needs fewer active-set rounds."""
+    n = 256
+    st = synthetic.make_states(n, GHOST, seed=9)
+    robots = [SyntheticRobotBatch(GHOST, st, device=cuda_device) for _ in range(2)]
+    clock = torch.zeros(n, dtype=torch.float64, device=cuda_device)
+    ctl = [BatchedMPCController(robots[0], lambda: clock, warm_start=True), BatchedMPCController(robots[1], lambda: clock, warm_start=False)]
+    assert ctl[0].mpc_active_set is not None and ctl[1].mpc_active_set is None
+    cmd = torch.tensor([[0.2, 0.0, 0.1]] * n)
+    for c in ctl:
+        c.update_controller_params(cmd)
+    rng = np.random.default_rng(1)
+    rounds = np.zeros(2)
+    for step in range(30):
+        clock += 0.002
+        drift = torch.from_numpy(rng.normal(0, 0.003, (n, 3)).astype(np.float32)).to(cuda_device)
+        for r in robots:
+            r.base_velocity_world += drift
+            r.base_rpy[:, :2] += 0.1 * drift[:, :2]
+        acts = [c.get_action().clone() for c in ctl]
+        torch.cuda.synchronize()
+        a0, a1 = acts[0].cpu().numpy(), acts[1].cpu().numpy()
+        assert np.abs(a0 - a1).max() < 1e-4 * max(1.0, np.abs(a1).max()), step
+        for k, c in enumerate(ctl):
+            info = c.solve_info.cpu().numpy()
+            assert np.all((info[:, rg.RG_INFO_STATUS] & (rg.RG_STATUS_POLISHED | rg.RG_STATUS_NO_STANCE)) != 0)
+            if step > 0:
+                rounds[k] += info[:, rg.RG_INFO_POLISH_ROUNDS].mean()
+    assert rounds[0] < 0.8 * rounds[1], rounds
+    ctl[0].reset(torch.tensor([0, 5], device=cuda_device))
+    assert int(ctl[0].mpc_active_set[5, 0]) == -1 and int(ctl[0].mpc_active_set[5].max()) == -1

@@ -207,3 +207,48 @@ def test_solver_paths_agree(rg_lib, cuda_device, schedule):
     assert not np.any(info_deep[:, rg.RG_INFO_STATUS] & rg.RG_STATUS_POLISHED)
     # same active-set size reported by both verified routes
     assert np.array_equal(info_cold[:, rg.RG_INFO_NUM_ACTIVE], info_ipm[:, rg.RG_INFO_NUM_ACTIVE])
+
+
+def test_warm_start_is_result_neutral_and_saves_rounds(rg_lib, cuda_device):
+    """rg_mpc_build_solve_warm: seeding the active-set iteration with the set verified by the previous solve of
+    the same env must not change the forces (unique optimum) and should verify in one round when the problem
+    repeats; a slightly perturbed problem still verifies, a garbage seed is repaired, swing blocks and
+    unverified solves leave RG_ACTIVE_SET_UNKNOWN behind."""
+    st = synthetic.make_states(1024, GHOST, seed=51)
+    ctrl = GHOST.GetCtrlConstants()
+    p = rg.default_mpc_params(ctrl.MPC_BODY_MASS, ctrl.MPC_BODY_INERTIA, ctrl.MPC_BODY_HEIGHT, 10)
+    ws = rg.MpcWorkspace(p, device=cuda_device)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    args = lambda s: (t(s.com_velocity_body), t(s.base_rpy), t(s.base_rpy_rate), t(s.planned_contacts), t(s.foot_positions_base), t(s.command))
+    f_cold, _, info_cold = rg.mpc_build_solve(ws, *args(st))
+    seed = rg.new_active_set(1024, 10, cuda_device)
+    f1, _, info1 = rg.mpc_build_solve(ws, *args(st), active_set=seed)          # unknown seed == cold start
+    torch.cuda.synchronize()
+    assert torch.equal(f1, f_cold) and torch.equal(info1, info_cold)
+    stored = seed.cpu().numpy().astype(np.int64) & 0xFFFF
+    swing = np.repeat(st.planned_contacts[:, None, :] == 0, 10, axis=1).reshape(1024, 40)
+    assert np.all(stored[swing] == 0xFFFF) and np.all(stored[~swing] <= 0x3FF)
+    nact = np.array([sum(bin(int(v)).count("1") for v in row if v != 0xFFFF) for row in stored])
+    assert np.array_equal(nact, info_cold.cpu().numpy()[:, rg.RG_INFO_NUM_ACTIVE])
+    f2, _, info2 = rg.mpc_build_solve(ws, *args(st), active_set=seed)          # same problem, exact seed
+    torch.cuda.synchronize()
+    i2 = info2.cpu().numpy()
+    assert np.abs((f2 - f_cold).cpu().numpy()).max() < 1e-4 * max(1.0, float(f_cold.abs().max()))
+    assert np.all(i2[:, rg.RG_INFO_POLISH_ROUNDS] == 1) and np.all(i2[:, rg.RG_INFO_IPM_ITERS] == 0)
+    # a neighbouring problem (next control step: state drifts a little)
+    rng = np.random.default_rng(0)
+    st2 = st.slice(0, 1024)
+    st2.com_velocity_body = (st.com_velocity_body + rng.normal(0, 0.01, st.com_velocity_body.shape)).astype(np.float32)
+    st2.base_rpy = (st.base_rpy + rng.normal(0, 0.002, st.base_rpy.shape) * np.array([1, 1, 0])).astype(np.float32)
+    f3, _, info3 = rg.mpc_build_solve(ws, *args(st2), active_set=seed)
+    f3c, _, info3c = rg.mpc_build_solve(ws, *args(st2))
+    torch.cuda.synchronize()
+    assert np.abs((f3 - f3c).cpu().numpy()).max() < 1e-4 * max(1.0, float(f3c.abs().max()))
+    assert np.all(info3.cpu().numpy()[:, rg.RG_INFO_STATUS] & rg.RG_STATUS_POLISHED)
+    assert info3.cpu().numpy()[:, rg.RG_INFO_POLISH_ROUNDS].mean() < info3c.cpu().numpy()[:, rg.RG_INFO_POLISH_ROUNDS].mean()
+    # a garbage seed (every row of every block marked active) is repaired
+    junk = torch.full((1024, 40), 0x3FF, dtype=torch.int16, device=cuda_device)
+    f4, _, info4 = rg.mpc_build_solve(ws, *args(st), active_set=junk)
+    torch.cuda.synchronize()
+    assert np.all(info4.cpu().numpy()[:, rg.RG_INFO_STATUS] & rg.RG_STATUS_POLISHED)
+    assert np.abs((f4 - f_cold).cpu().numpy()).max() < 1e-4 * max(1.0, float(f_cold.abs().max()))

@@ -3,7 +3,8 @@
     python tools/bench_configs.py [out.json]
 
 config 2: 4096 envs MPC stance solve (h = 10), gait-derived and all-stance contacts
-config 3: 65536 envs full control step (gait + estimator + swing + IK + MPC + pack)
+config 3: 65536 envs full control step (gait + estimator + swing + IK + MPC + pack); cold = every QP from scratch,
+          warm_start = seeded with the previous step's verified active set (static synthetic states: best case)
 config 4: horizon 5/10/20 x {trot, pace, bound, walk} contact schedules, 65536 envs, MPC solve
 config 5: the MPC solve at 2^20 envs on ONE GPU (the whole config-5 batch) and at 2^17 (one rank's share of it on 8 GPUs)
 light   : rg_state_from_sim / rg_hybrid_motor_torque at 2^20 envs against the HBM roofline
@@ -49,14 +50,15 @@ def mpc_case(n, horizon, schedule, all_stance=False, reps=10):
             "polished_fraction": float(np.mean((inf[:, 2] & 1) != 0)), "stance_legs_mean": float(st.planned_contacts.sum(axis=1).mean())}
 
 
-def control_case(n, reps, warm):
+def control_case(n, reps, warm, warm_start=False):
     st = synthetic.make_states(n, GHOST)
     robot = SyntheticRobotBatch(GHOST, st)
-    ctl = BatchedMPCController(robot, robot.GetTimeSinceReset, squeeze_single=False)
+    ctl = BatchedMPCController(robot, robot.GetTimeSinceReset, squeeze_single=False, warm_start=warm_start)
     ctl.command.copy_(torch.from_numpy(st.command).cuda())
     ms = sorted(time_ms(ctl.step, reps, warm))
     p50, p99 = ms[len(ms) // 2], ms[min(len(ms) - 1, int(0.99 * len(ms)))]
-    return {"envs": n, "p50_ms": p50, "p99_ms": p99, "env_steps_per_s": n / p50 * 1e3, "launches_per_step": 3}
+    return {"envs": n, "warm_start": warm_start, "p50_ms": p50, "p99_ms": p99, "env_steps_per_s": n / p50 * 1e3, "launches_per_step": 3,
+            "active_set_rounds_mean": float(ctl.solve_info[:, rg.RG_INFO_POLISH_ROUNDS].to(torch.float64).mean())}
 
 
 def light_kernel_cases(n):
@@ -93,9 +95,9 @@ def light_kernel_cases(n):
 def main():
     out = {"gpu": torch.cuda.get_device_name(0), "library": rg.load().rg_version().decode()}
     out["config2_mpc_4096"] = [mpc_case(4096, 10, "trot"), mpc_case(4096, 10, "trot", all_stance=True)]
-    out["config3_control_step_65536"] = control_case(65536, 10, 3)
+    out["config3_control_step_65536"] = [control_case(65536, 10, 3), control_case(65536, 10, 3, warm_start=True)]
     out["config4_horizon_x_schedule_65536"] = [mpc_case(65536 if h < 20 else 16384, h, s, reps=5) for h in (5, 10, 20) for s in ("trot", "pace", "bound", "walk")]
-    out["latency_control_step"] = [control_case(n, 200 if n < 65536 else 30, 20 if n < 65536 else 3) for n in (1, 4096, 65536)]
+    out["latency_control_step"] = [control_case(n, 200 if n < 65536 else 30, 20 if n < 65536 else 3, warm_start=w) for n in (1, 4096, 65536) for w in (False, True)]
     out["config5_single_gpu_share_of_2p20_envs"] = [mpc_case(1 << 20, 10, "trot", reps=3), mpc_case(1 << 17, 10, "trot", reps=5)]
     out["light_kernels_hbm"] = light_kernel_cases(1 << 20)
     out["fma_peak_tflops"] = {"fp64": rg.measure_fma_peak(True), "fp32": rg.measure_fma_peak(False)}
