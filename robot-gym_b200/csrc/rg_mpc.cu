@@ -1229,14 +1229,17 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 #pragma unroll
         for (int d = 0; d < 3; ++d) gr[d] = pu[d] + q[d];
       }
-      // Pass 0 is the solve, pass 1 one step of iterative refinement.  The active set is checked after
+      // Pass 0 is the solve, passes 1-2 steps of iterative refinement.  The active set is checked after
       // each: when it moves after pass 0 the refinement would be wasted (the next round starts over),
       // and it is skipped as well when pass 0 already left a projected gradient at rounding level.
+      // A verdict on the set is only taken from a solve that is accurate enough to give it (projected
+      // gradient <= 1e-9 |q|): with many active rows at h = 20 a single refinement step can leave 1e-9,
+      // above the multiplier-sign threshold, and one weakly active row then flips in and out for ever.
       unsigned act_new = act;
       double nchg = 0.0, ncone = 0.0, pgm = 0.0;
       bool accept = false;
 #pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
+      for (int pass = 0; pass < 3; ++pass) {
         double ng[3], bprime[3], dx[3], pu[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) ng[d] = -gr[d];
@@ -1290,8 +1293,9 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
         ncone = floor(nchg * (1.0 / 4096.0));
         nchg -= 4096.0 * ncone;
         RG_TOC(24);
-        if (nchg > 0.0) break;
-        if (pgm <= (pass == 0 ? RG_SKIP_REFINE_TOL : 1e-7) * qscale) { accept = true; break; }
+        const bool trusted = pgm <= 1e-9 * qscale || pass == 2;
+        if (nchg > 0.0) { if (trusted) break; else continue; }
+        if (pgm <= (pass == 0 ? RG_SKIP_REFINE_TOL : pass == 1 ? 1e-10 : 1e-7) * qscale) { accept = true; break; }
       }
 #ifdef RG_DEBUG_TRACE
       {

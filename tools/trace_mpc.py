@@ -25,17 +25,24 @@ PHASES = {8: "setup (inputs, tables, K^-1)", 40: "  setup: input loads, sincos",
 
 def main():
     envs = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3]
+    find_unpolished = os.environ.get("RG_TRACE_FIND_UNPOLISHED") == "1"
     lib = rg.load()
     lib.rg_debug_set_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
     ctrl = GHOST.GetCtrlConstants()
-    p = rg.default_mpc_params(ctrl.MPC_BODY_MASS, ctrl.MPC_BODY_INERTIA, ctrl.MPC_BODY_HEIGHT, 10)
+    p = rg.default_mpc_params(ctrl.MPC_BODY_MASS, ctrl.MPC_BODY_INERTIA, ctrl.MPC_BODY_HEIGHT, int(os.environ.get("RG_TRACE_H", "10")))
     ws = rg.MpcWorkspace(p)
     n = int(os.environ.get("RG_TRACE_N", "65536"))     # batch the env index refers to (make_states(n) draws depend on n)
     gait = os.environ.get("RG_TRACE_GAIT", "trot")
-    st = synthetic.make_states(n, GHOST if gait == "trot" else with_gait(GHOST, gait))
+    desc = GHOST if gait == "trot" else with_gait(GHOST, gait)
+    st = synthetic.make_states(n, desc, schedule_ctrl=desc.GetCtrlConstants())
     t = lambda a: torch.from_numpy(a).cuda()
     full = (t(st.com_velocity_body), t(st.base_rpy), t(st.base_rpy_rate), t(st.planned_contacts), t(st.foot_positions_base), t(st.command))
     trace = torch.zeros(1024, dtype=torch.float64, device="cuda")
+    if find_unpolished:
+        _, _, info_all = rg.mpc_build_solve(ws, *full)
+        ia = info_all.cpu().numpy()
+        envs = list(np.flatnonzero((ia[:, 2] & 1) == 0)[:3])
+        print("unpolished envs:", envs, ia[envs])
     for e in envs:
         for label, lo, cnt, idx in (("solo", e, 1, 0), ("loaded", 0, n, e))[:1 if os.environ.get("RG_TRACE_SOLO") else 2]:
             args = tuple(a[lo:lo + cnt].contiguous() for a in full)
