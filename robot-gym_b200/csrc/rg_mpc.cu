@@ -125,6 +125,9 @@ __device__ __forceinline__ double c1f(int h, int j, int k) { return (double)(h -
 #ifndef RG_IPM_RD_SCALE
 #define RG_IPM_RD_SCALE 1.0
 #endif
+#ifndef RG_IPM_SLOW_ITERS
+#define RG_IPM_SLOW_ITERS 5
+#endif
 // cold start: fz >= fz_min is guessed active in the last RG_COLD_GUESS_LAST steps of the horizon (0 = empty set)
 #ifndef RG_COLD_GUESS_LAST
 #define RG_COLD_GUESS_LAST 1
@@ -945,7 +948,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   (void)trace_n;
   double best_res = 1e300, prev_res = 1e300;
   double u_best[3] = {u[0], u[1], u[2]};
-  int stall = 0;
+  int stall = 0, slow = 0;
   bool done = false;
   // Attempt -1 is the cold start: the same active-set iteration started from the empty set (round 0
   // is the unconstrained minimiser), with no interior point before it.  Most trot-like problems have
@@ -955,7 +958,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   const double cold_max_viol = (double)ws->cold_start_max_violations;
 #pragma unroll 1
   for (int attempt = cold_rounds > 0 ? -1 : 0; attempt < 3 && !done; ++attempt) {
-    bool converged = false, ipm_dead = false;
+    bool converged = false, ipm_dead = false, handed_over = false;
     const bool cold = attempt < 0;
     if (!cold) {
     if (iters == 0) {
@@ -998,12 +1001,17 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       const double res = fmax(rdmax, mu_c) / qscale;
       RG_TRACE(4 * trace_n + 0, res); RG_TRACE(4 * trace_n + 1, mu_c); RG_TRACE(4 * trace_n + 2, (double)iters); RG_TRACE(4 * trace_n + 3, tol);
       ++trace_n;
+      // slow lane: the best residual has not halved for RG_IPM_SLOW_ITERS iterations although the iterate is
+      // already close (mu oscillating around 1e-5 on a few pace / bound problems, 40 iterations to the cap):
+      // hand over to the active-set rounds, which verify from such a point in a round or two
+      slow = (res < 0.5 * best_res) ? 0 : slow + 1;
       if (res < best_res) {
         best_res = res;
 #pragma unroll
         for (int d = 0; d < 3; ++d) u_best[d] = u[d];
       }
       if (res < tol) { converged = true; break; }
+      if (slow >= RG_IPM_SLOW_ITERS && res < 1e-3 && max_polish > 0) { handed_over = true; slow = 0; break; }
       stall = (res > 0.9 * prev_res && res < 1e-7) ? stall + 1 : 0;   // only near the numerical floor
       prev_res = res;
       // dead: budget spent, stalled at the numerical floor, NaN, or diverging (deep iterates lose the
@@ -1133,7 +1141,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     double prev_nchg = 1e300;
     double up[3] = {0.0, 0.0, 0.0};
     // 3, 6, 12 rounds: later attempts start from a sharper guess; a dead interior point gets the full budget
-    const int round_budget = cold ? cold_rounds + RG_COLD_EXTEND_ROUNDS : ipm_dead ? (max_polish << 2) : (max_polish << attempt);
+    const int round_budget = cold ? cold_rounds + RG_COLD_EXTEND_ROUNDS : (ipm_dead || handed_over) ? (max_polish << 2) : (max_polish << attempt);
 #pragma unroll 1
     for (int round = 0; round < round_budget; ++round) {
       ++polish_rounds;

@@ -41,8 +41,8 @@ def main():
     if find_unpolished:
         _, _, info_all = rg.mpc_build_solve(ws, *full)
         ia = info_all.cpu().numpy()
-        envs = list(np.flatnonzero((ia[:, 2] & 1) == 0)[:3])
-        print("unpolished envs:", envs, ia[envs])
+        envs = list(np.flatnonzero((ia[:, 2] & 1) == 0)[:3]) + list(np.argsort(-ia[:, 0])[:2])
+        print("unpolished / slowest envs:", envs, ia[envs])
     for e in envs:
         for label, lo, cnt, idx in (("solo", e, 1, 0), ("loaded", 0, n, e))[:1 if os.environ.get("RG_TRACE_SOLO") else 2]:
             args = tuple(a[lo:lo + cnt].contiguous() for a in full)
