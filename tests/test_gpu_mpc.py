@@ -74,7 +74,7 @@ def test_forces_match_live_oracle_on_seeded_states(rg_lib, cuda_device):
         assert _rel(hf[i].reshape(-1), ref) < REL_TOL, i
 
 
-@pytest.mark.parametrize("case", ["all_stance", "weights2", "mu_rows", "explicit_height", "alpha_small"])
+@pytest.mark.parametrize("case", ["all_stance", "weights2", "mu_rows", "explicit_height", "alpha_small", "heavy_robot", "dt_short"])
 def test_forces_match_oracle_parameter_variants(rg_lib, cuda_device, case):
     st = synthetic.make_states(48, GHOST, all_stance=(case == "all_stance"), seed=123)
     overrides, kw, com_h = {}, {}, False
@@ -88,6 +88,12 @@ def test_forces_match_oracle_parameter_variants(rg_lib, cuda_device, case):
         com_h = True
     if case == "alpha_small":
         overrides["alpha"], kw["alpha"] = 1e-6, 1e-6
+    if case == "heavy_robot":    # a different body (mass, full inertia tensor with products of inertia, fz bounds follow the mass)
+        mass, inertia = 31.0, (0.21, 0.01, -0.02, 0.01, 0.62, 0.015, -0.02, 0.015, 0.71)
+        overrides.update(mass=mass, inertia=inertia, fz_max=mass * 9.8 * 10.0, fz_min=mass * 9.8 * 0.1)
+        kw.update(mass=mass, inertia=inertia)
+    if case == "dt_short":       # planning step of the other recalled configuration
+        overrides["dt"], kw["dt"] = 0.03, 0.03
     f, hf, info, _ = _run(rg_lib, cuda_device, st, overrides=overrides, com_height=com_h)
     for i in range(0, 48, 3):
         ref = _oracle(st, i, com_height=com_h, **kw)
