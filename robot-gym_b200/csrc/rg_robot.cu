@@ -27,9 +27,8 @@ __host__ __device__ inline V3 mat_tmul(const double* m, V3 v) {  // M^T v
   return v3(m[0] * v.x + m[3] * v.y + m[6] * v.z, m[1] * v.x + m[4] * v.y + m[7] * v.z, m[2] * v.x + m[5] * v.y + m[8] * v.z);
 }
 // Rodrigues rotation of v about the unit axis a by angle q
-__host__ __device__ inline V3 rot_axis(V3 a, double q, V3 v) {
-  double s, c;
-  sincos(q, &s, &c);
+// Rodrigues rotation of v about the unit axis a by the angle whose sine / cosine are (s, c)
+__host__ __device__ inline V3 rot_sc(V3 a, double s, double c, V3 v) {
   return add(add(mul(c, v), mul(s, cross(a, v))), mul((1.0 - c) * dot(a, v), a));
 }
 __host__ __device__ inline double wrap_pi(double a) {
@@ -42,26 +41,40 @@ __host__ __device__ inline double wrap_pi(double a) {
 // ------------------------------------------------------------------------------------ kinematics
 // foot = p0 + R0 Rot(a0,q0) ( p1 + R1 Rot(a1,q1) ( p2 + R2 Rot(a2,q2) toe ) ), base frame.
 // Also returns the translational Jacobian columns (axis_world x (foot - origin_world)).
+// FAST_TRIG: single-precision sincosf of the (float32) joint angles -- 1e-7 absolute on a 0.5 m chain, below
+// the float32 output resolution; used by the state provider, whose cost is otherwise all FP64 trigonometry.
+template <bool FAST_TRIG = false>
 __host__ __device__ inline V3 leg_fk(const RgLegDev& L, const double* q, V3* jac /* 3 columns or nullptr */) {
   const V3 a0 = ld3(L.axis[0]), a1 = ld3(L.axis[1]), a2 = ld3(L.axis[2]);
+  double sn[3], cs[3];   // one sine / cosine per joint, shared by every rotation below
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (FAST_TRIG) {
+      float sf, cf;
+      sincosf((float)q[j], &sf, &cf);
+      sn[j] = sf; cs[j] = cf;
+    } else {
+      sincos(q[j], &sn[j], &cs[j]);
+    }
+  }
   // innermost first
-  V3 v2 = rot_axis(a2, q[2], ld3(L.toe));                   // in joint-2 frame
+  V3 v2 = rot_sc(a2, sn[2], cs[2], ld3(L.toe));             // in joint-2 frame
   V3 w2 = add(ld3(L.p[2]), mat_mul(L.r[2], v2));            // in link-1 frame (joint-1 frame after rotation)
-  V3 v1 = rot_axis(a1, q[1], w2);
+  V3 v1 = rot_sc(a1, sn[1], cs[1], w2);
   V3 w1 = add(ld3(L.p[1]), mat_mul(L.r[1], v1));            // in link-0 frame
-  V3 v0 = rot_axis(a0, q[0], w1);
+  V3 v0 = rot_sc(a0, sn[0], cs[0], w1);
   V3 foot = add(ld3(L.p[0]), mat_mul(L.r[0], v0));
   if (jac) {
     // world (base) frame axes and origins
     const V3 ax0 = mat_mul(L.r[0], a0);
     const V3 o0 = ld3(L.p[0]);
     // F0 x = R0 Rot0 x
-    const V3 o1 = add(o0, mat_mul(L.r[0], rot_axis(a0, q[0], ld3(L.p[1]))));
-    const V3 ax1 = mat_mul(L.r[0], rot_axis(a0, q[0], mat_mul(L.r[1], a1)));
-    const V3 p2_l0 = mat_mul(L.r[1], rot_axis(a1, q[1], ld3(L.p[2])));           // in link-0 frame
-    const V3 o2 = add(o1, mat_mul(L.r[0], rot_axis(a0, q[0], p2_l0)));
-    const V3 ax2_l0 = mat_mul(L.r[1], rot_axis(a1, q[1], mat_mul(L.r[2], a2)));
-    const V3 ax2 = mat_mul(L.r[0], rot_axis(a0, q[0], ax2_l0));
+    const V3 o1 = add(o0, mat_mul(L.r[0], rot_sc(a0, sn[0], cs[0], ld3(L.p[1]))));
+    const V3 ax1 = mat_mul(L.r[0], rot_sc(a0, sn[0], cs[0], mat_mul(L.r[1], a1)));
+    const V3 p2_l0 = mat_mul(L.r[1], rot_sc(a1, sn[1], cs[1], ld3(L.p[2])));           // in link-0 frame
+    const V3 o2 = add(o1, mat_mul(L.r[0], rot_sc(a0, sn[0], cs[0], p2_l0)));
+    const V3 ax2_l0 = mat_mul(L.r[1], rot_sc(a1, sn[1], cs[1], mat_mul(L.r[2], a2)));
+    const V3 ax2 = mat_mul(L.r[0], rot_sc(a0, sn[0], cs[0], ax2_l0));
     jac[0] = cross(ax0, sub(foot, o0));
     jac[1] = cross(ax1, sub(foot, o1));
     jac[2] = cross(ax2, sub(foot, o2));
@@ -300,7 +313,7 @@ __global__ void state_from_sim_kernel(const RgRobotDev* __restrict__ R, int n_en
     if (motor_angles) motor_angles[12 * (size_t)env + m] = (float)((q[j] - R->motor_offset[m]) * R->motor_direction[m]);
   }
   if (foot) {
-    const V3 f = leg_fk(R->legs[leg], q, nullptr);
+    const V3 f = leg_fk<true>(R->legs[leg], q, nullptr);
     foot[3 * (size_t)idx] = (float)f.x; foot[3 * (size_t)idx + 1] = (float)f.y; foot[3 * (size_t)idx + 2] = (float)f.z;
   }
   if (leg != 0) return;
@@ -310,12 +323,13 @@ __global__ void state_from_sim_kernel(const RgRobotDev* __restrict__ R, int n_en
     const double sqx = qx * qx, sqy = qy * qy, sqz = qz * qz, sqw = qw * qw;
     const double sarg = -2.0 * (qx * qz - qw * qy);
     double roll, pitch, yaw;
-    if (sarg <= -0.99999) { pitch = -0.5 * 3.14159265358979323846; roll = 0.0; yaw = 2.0 * atan2(qx, -qy); }
-    else if (sarg >= 0.99999) { pitch = 0.5 * 3.14159265358979323846; roll = 0.0; yaw = 2.0 * atan2(-qx, qy); }
+    // single-precision inverse trigonometry on double-precision arguments: the outputs are float32
+    if (sarg <= -0.99999) { pitch = -0.5 * 3.14159265358979323846; roll = 0.0; yaw = 2.0 * atan2f((float)qx, (float)-qy); }
+    else if (sarg >= 0.99999) { pitch = 0.5 * 3.14159265358979323846; roll = 0.0; yaw = 2.0 * atan2f((float)-qx, (float)qy); }
     else {
-      roll = atan2(2.0 * (qy * qz + qw * qx), sqw - sqx - sqy + sqz);
-      pitch = asin(sarg);
-      yaw = atan2(2.0 * (qx * qy + qw * qz), sqw + sqx - sqy - sqz);
+      roll = atan2f((float)(2.0 * (qy * qz + qw * qx)), (float)(sqw - sqx - sqy + sqz));
+      pitch = asinf((float)sarg);
+      yaw = atan2f((float)(2.0 * (qx * qy + qw * qz)), (float)(sqw + sqx - sqy - sqz));
     }
     rpy[3 * (size_t)env] = (float)roll; rpy[3 * (size_t)env + 1] = (float)pitch; rpy[3 * (size_t)env + 2] = (float)yaw;
   }
