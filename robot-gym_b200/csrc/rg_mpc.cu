@@ -128,6 +128,12 @@ __device__ __forceinline__ double c1f(int h, int j, int k) { return (double)(h -
 #ifndef RG_IPM_SLOW_ITERS
 #define RG_IPM_SLOW_ITERS 5
 #endif
+// Cholesky: idle lower-half threads take half of each late panel's dot products (see cholesky_rows).
+// OFF: it shortens a factorisation alone on an SM but measured 3-6 % slower with 8 CTAs per SM (the
+// launch is throughput-bound there; a warp parked at a barrier costs nothing, a helper warp does).
+#ifndef RG_CHOL_HELPERS
+#define RG_CHOL_HELPERS 0
+#endif
 // cold start: fz >= fz_min is guessed active in the last RG_COLD_GUESS_LAST steps of the horizon (0 = empty set)
 #ifndef RG_COLD_GUESS_LAST
 #define RG_COLD_GUESS_LAST 1
@@ -188,6 +194,14 @@ __device__ __forceinline__ double quad_sum(double v) {   // sum over the 4 legs 
 template <int H>
 __device__ __noinline__ void cholesky_rows(Smem<H>& sm, int j_begin) {
   constexpr int N6 = Cfg<H>::N6;
+  constexpr int HALF = Cfg<H>::NT / 2;
+  // Helper threads (RG_CHOL_HELPERS): once the panel has moved past row HALF the lower half of the CTA owns
+  // no row in play, so thread t < HALF takes the FIRST half of the k-range of row HALF + t and the row's own
+  // thread the second half.  Both run the same uniform loop (same trip count, uniform panel-row bases) and
+  // differ only in a per-thread start offset.  Partial sums travel through sm.avec / sm.kvec, which hold
+  // nothing live during a factorisation.
+  constexpr bool kHelpers = RG_CHOL_HELPERS && Cfg<H>::NW >= 2 && 4 * (N6 - HALF) <= 12 * H;
+  double* part = sm.avec;
   const int i = threadIdx.x;
   const bool row_ok = i < N6;
   double* row_i = sm.psi + prow(row_ok ? i : 0);
@@ -199,17 +213,23 @@ __device__ __noinline__ void cholesky_rows(Smem<H>& sm, int j_begin) {
     const int w = N6 - j0 < 4 ? N6 - j0 : 4;          // panel width (the last panel of N6 = 30 has 2 columns)
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     const bool in_play = row_ok && i >= j0;
-    if (in_play) {
-      const double* r2 = row_i;
-      const double* p0 = sm.psi + prow(j0);
-      const double* p1 = sm.psi + prow(j0 + (w > 1 ? 1 : 0));
-      const double* p2 = sm.psi + prow(j0 + (w > 2 ? 2 : 0));
-      const double* p3 = sm.psi + prow(j0 + (w > 3 ? 3 : 0));
+    const bool helper_mode = kHelpers && j0 >= HALF;  // uniform
+    const bool is_helper = helper_mode && i < HALF;
+    const int wrow = is_helper ? i + HALF : i;        // the row this thread accumulates for
+    if (is_helper ? (wrow >= j0 && wrow < N6) : in_play) {
+      const int ng = helper_mode ? (j0 >> 2) : (j0 >> 1);   // pair-steps per thread (uniform); j0 % 4 == 0
+      const int off = (helper_mode && !is_helper) ? (j0 >> 1) : 0;   // the row thread starts at column j0 / 2
+      const double* r2 = sm.psi + prow(wrow) + off;
+      const double* p0 = sm.psi + prow(j0) + off;
+      const double* p1 = sm.psi + prow(j0 + (w > 1 ? 1 : 0)) + off;
+      const double* p2 = sm.psi + prow(j0 + (w > 2 ? 2 : 0)) + off;
+      const double* p3 = sm.psi + prow(j0 + (w > 3 ? 3 : 0)) + off;
+      if (!is_helper) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[c] = (c < w && j0 + c <= i) ? row_i[j0 + c] : 0.0;
-      // software-pipelined dot products: the 128-bit loads of step g+1 are in flight while step g's
+        for (int c = 0; c < 4; ++c) acc[c] = (c < w && j0 + c <= i) ? row_i[j0 + c] : 0.0;
+      }
+      // software-pipelined dot products: the loads of step g+1 are in flight while step g's
       // eight FMAs retire (the loop is latency-bound on shared memory otherwise: 2 warps per CTA)
-      const int ng = j0 >> 1;                          // pairs of columns already factored (j0 % 4 == 0)
       double2 a = ld2(r2), b0 = ld2(p0), b1 = ld2(p1), b2 = ld2(p2), b3 = ld2(p3);
 #pragma unroll 2
       for (int g = 0; g < ng; ++g) {
@@ -221,7 +241,10 @@ __device__ __noinline__ void cholesky_rows(Smem<H>& sm, int j_begin) {
         acc[2] = fma(-a.y, b2.y, acc[2]); acc[3] = fma(-a.y, b3.y, acc[3]);
         a = an; b0 = c0; b1 = c1; b2 = c2; b3 = c3;
       }
-      if (i < j0 + w) {                                // a panel row: publish the updated entries A'[i][j0..i]
+      if (is_helper) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) part[4 * i + c] = acc[c];
+      } else if (i < j0 + w) {                         // a panel row: publish the updated entries A'[i][j0..i]
         // into the side buffer, NOT into Psi: phase 2 overwrites the panel rows of Psi with the factor
         // while other warps may still be reading the block (that was a cross-warp race)
 #pragma unroll
@@ -237,8 +260,15 @@ __device__ __noinline__ void cholesky_rows(Smem<H>& sm, int j_begin) {
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c <= r; ++c)
-          a[r][c] = (r < w) ? sm.blk44[4 * r + c] : (r == c ? 1.0 : 0.0);
+        for (int c = 0; c <= r; ++c) a[r][c] = (r < w) ? sm.blk44[4 * r + c] : (r == c ? 1.0 : 0.0);
+      if (helper_mode) {                               // add the helpers' halves (block rows and own row)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c <= r; ++c) if (r < w) a[r][c] += part[4 * (j0 + r - HALF) + c];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[c] += part[4 * (i - HALF) + c];
+      }
       // factor: l[r][c] for c < r, inverse diagonal in rd[r]
       double rd[4];
       bool bad = false;
@@ -1441,10 +1471,11 @@ __global__ void __launch_bounds__(Cfg<H>::NT) chol_selftest_kernel(const double*
   const int tid = threadIdx.x;
   if (tid < N6) {
     for (int k = 0; k <= tid; ++k) sm.psi[prow(tid) + k] = a_dense[tid * N6 + k];
-    sm.avec[tid] = rhs[tid];
   }
   __syncthreads();
   cholesky_rows<H>(sm, 0);
+  if (tid < N6) sm.avec[tid] = rhs[tid];   // after the factorisation: avec / kvec are its scratch
+  __syncthreads();
   if (tid < 32) tri_solve_warp0<H>(sm);
   __syncthreads();
   if (tid < N6) {
