@@ -982,7 +982,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   bool done = false;
   // Attempt -1 is the cold start: the same active-set iteration started from the empty set (round 0
   // is the unconstrained minimiser), with no interior point before it.  Most trot-like problems have
-  // a handful of active rows and verify within 2-3 rounds (DESIGN.md 3.7); the ones that do not fall
+  // a handful of active rows and verify within 2-3 rounds (DESIGN.md 3.3); the ones that do not fall
   // through to the interior point untouched.
   const int cold_rounds = ws->cold_start_rounds;
   const double cold_max_viol = (double)ws->cold_start_max_violations;
@@ -1236,7 +1236,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       RG_TOC(20);
       // Only the time steps from the first block whose active set moved since the last factorisation
       // change Psi, and a left-looking Cholesky keeps its leading columns: refactor the tail only
-      // (active rows cluster at the end of the horizon: DESIGN.md 3.7).
+      // (active rows cluster at the end of the horizon: DESIGN.md 3.3).
       {
         double dsum = 0.0, dmx = 0.0, tmin = (double)H;
         if (active_blk && act != act_fact) tmin = (double)t_blk;
