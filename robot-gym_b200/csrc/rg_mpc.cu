@@ -125,6 +125,9 @@ __device__ __forceinline__ double c1f(int h, int j, int k) { return (double)(h -
 #ifndef RG_IPM_RD_SCALE
 #define RG_IPM_RD_SCALE 1.0
 #endif
+#ifndef RG_IPM_TAU_LATE
+#define RG_IPM_TAU_LATE 0.99
+#endif
 #ifndef RG_IPM_SLOW_ITERS
 #define RG_IPM_SLOW_ITERS 5
 #endif
@@ -1127,9 +1130,10 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
         if (active_blk) tmax = fmax(tmax, fmax(-yr[r], wv[r] * (s[r] * isl[r]) + yr[r]));
       }
       block_reduce<C::NW>(dsum, tmax, dmn2, sm.red);
-      // fraction to the boundary: 0.99 far out, 0.999 once both residuals are small (a step closer to 1
-      // collapses the slacks while the dual residual is still finite and de-centres the iterate)
-      const double tau = res < 1e-3 ? 0.999 : 0.99;
+      // fraction to the boundary: 0.99 throughout.  (0.999 once the residuals are small saved nothing measurable
+      // and made two bound-gait problems in 1.5 M oscillate at mu ~ 1e-4; steps closer to 1 collapse the slacks
+      // while the dual residual is still finite and de-centre the iterate.)
+      const double tau = res < 1e-3 ? RG_IPM_TAU_LATE : 0.99;
       const double step = tmax > tau ? tau / tmax : 1.0;
       if (active_blk) {
 #pragma unroll
@@ -1311,12 +1315,19 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
             for (int k = i + 1; k < na; ++k) v -= rr[i][k] * y[k];
             y[i] = v / rr[i][i];
           }
+          double ymin = 1e300;
+          int imin = -1;
 #pragma unroll 1
           for (int i = 0; i < na; ++i) {
             // upper-bound rows need y >= 0, lower-bound rows y <= 0
             const double ysgn = rows[i] < 5 ? y[i] : -y[i];
             if (ysgn < -1e-10 * qscale) act_new &= ~(1u << rows[i]);
+            if (ysgn < ymin) { ymin = ysgn; imin = i; }
           }
+          // a block that already holds three rows is a vertex: a violated fourth row can only come in if one
+          // leaves, and the basis builder keeps the first three in bit order -- without this swap the newcomer
+          // is dropped again next round and the same round repeats for ever.  The weakest multiplier leaves.
+          if (na == 3 && (act_new & ~act) != 0u && (act_new & act) == act) act_new &= ~(1u << rows[imin]);
         }
         // stationarity on the free subspace is what the solve is supposed to deliver; check it anyway so
         // that a wrong factorisation can never be reported as a verified optimum:  |Z Z^T (P u + q)|_inf

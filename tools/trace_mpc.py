@@ -34,14 +34,14 @@ def main():
     n = int(os.environ.get("RG_TRACE_N", "65536"))     # batch the env index refers to (make_states(n) draws depend on n)
     gait = os.environ.get("RG_TRACE_GAIT", "trot")
     desc = GHOST if gait == "trot" else with_gait(GHOST, gait)
-    st = synthetic.make_states(n, desc, schedule_ctrl=desc.GetCtrlConstants())
+    st = synthetic.make_states(n, desc, schedule_ctrl=desc.GetCtrlConstants(), seed=int(os.environ.get("RG_TRACE_SEED", str(synthetic.SEED))))
     t = lambda a: torch.from_numpy(a).cuda()
     full = (t(st.com_velocity_body), t(st.base_rpy), t(st.base_rpy_rate), t(st.planned_contacts), t(st.foot_positions_base), t(st.command))
     trace = torch.zeros(1024, dtype=torch.float64, device="cuda")
     if find_unpolished:
         _, _, info_all = rg.mpc_build_solve(ws, *full)
         ia = info_all.cpu().numpy()
-        envs = list(np.flatnonzero((ia[:, 2] & 1) == 0)[:3]) + list(np.argsort(-ia[:, 0])[:2])
+        envs = list(np.flatnonzero((ia[:, 2] & 1) == 0)[:3]) + (list(np.argsort(-ia[:, 0])[:2]) if os.environ.get("RG_TRACE_SLOWEST") else [])
         print("unpolished / slowest envs:", envs, ia[envs])
     for e in envs:
         for label, lo, cnt, idx in (("solo", e, 1, 0), ("loaded", 0, n, e))[:1 if os.environ.get("RG_TRACE_SOLO") else 2]:
