@@ -36,6 +36,21 @@ for sched, horizon in [("trot", 10), ("pace", 10), ("bound", 10), ("walk", 10), 
         torch.cuda.synchronize()
         unv = int((~ok).sum()); num = int(((status & 8) != 0).sum())
         tot["envs"] += m; tot["unverified"] += unv; tot["numeric"] += num
-        print(f"{sched:6s} h={horizon:2d} seed={seed} n={m}: unverified {unv} numeric {num} | swing |f| max {swing_max:.1e} | worst bound/cone violation {viol.item() / p.fz_max:.1e} x fz_max"
+        # warm-started re-solve of a neighbouring problem (the next control step): seeds from this solve
+        seedbuf = rg.new_active_set(m, horizon)
+        rg.mpc_build_solve(ws, t(st.com_velocity_body), t(st.base_rpy), t(st.base_rpy_rate), t(st.planned_contacts),
+                           t(st.foot_positions_base), t(st.command), active_set=seedbuf)
+        rng = np.random.default_rng(seed)
+        v2 = (st.com_velocity_body + rng.normal(0, 0.02, st.com_velocity_body.shape)).astype(np.float32)
+        rpy2 = (st.base_rpy + rng.normal(0, 0.005, st.base_rpy.shape) * np.array([1, 1, 0])).astype(np.float32)
+        fw, _, infow = rg.mpc_build_solve(ws, t(v2), t(rpy2), t(st.base_rpy_rate), t(st.planned_contacts), t(st.foot_positions_base), t(st.command), active_set=seedbuf)
+        fc, _, infoc = rg.mpc_build_solve(ws, t(v2), t(rpy2), t(st.base_rpy_rate), t(st.planned_contacts), t(st.foot_positions_base), t(st.command))
+        torch.cuda.synchronize()
+        warm_unv = int(((infow[:, 2] & 1) == 0).sum())
+        warm_gap = ((fw - fc).abs().max(dim=1).values / fc.abs().max(dim=1).values.clamp(min=1.0)).max().item()
+        tot["unverified"] += warm_unv
+        tot.setdefault("warm_gap_max", 0.0); tot["warm_gap_max"] = max(tot["warm_gap_max"], warm_gap)
+        tot.setdefault("warm_rounds", []).append((float(infow[:, 1].float().mean()), float(infoc[:, 1].float().mean())))
+        print(f"{sched:6s} h={horizon:2d} seed={seed} n={m}: unverified {unv} (warm {warm_unv}, warm-vs-cold gap {warm_gap:.1e}, rounds warm {infow[:,1].float().mean():.2f} / cold {infoc[:,1].float().mean():.2f}) numeric {num} | swing |f| max {swing_max:.1e} | worst bound/cone violation {viol.item() / p.fz_max:.1e} x fz_max"
               f" | ipm iters max {int(info[:,0].max())} rounds max {int(info[:,1].max())}")
-print("TOTAL", tot)
+wr = tot.pop("warm_rounds"); print("TOTAL", tot, "mean rounds warm/cold", np.mean([a for a, b in wr]).round(2), np.mean([b for a, b in wr]).round(2))
