@@ -73,7 +73,10 @@ struct Cfg {
 #ifndef RG_MIN_BLOCKS_H10
 #define RG_MIN_BLOCKS_H10 8
 #endif
-  static constexpr int MIN_BLOCKS = H <= 5 ? 16 : (H <= 10 ? RG_MIN_BLOCKS_H10 : 2);
+#ifndef RG_MIN_BLOCKS_H5
+#define RG_MIN_BLOCKS_H5 24
+#endif
+  static constexpr int MIN_BLOCKS = H <= 5 ? RG_MIN_BLOCKS_H5 : (H <= 10 ? RG_MIN_BLOCKS_H10 : 2);
 };
 
 template <int H>
