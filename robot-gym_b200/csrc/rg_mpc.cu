@@ -70,12 +70,19 @@ struct Cfg {
   static constexpr int NKA = NA * (NA + 1) / 2;
   static constexpr int RPL = (N6 + 31) / 32;   // Psi rows per lane in the triangular sweeps
   // resident CTAs per SM the register allocation is sized for (shared memory allows 9 / 2 at h = 10 / 20)
+// Cholesky panel width at h = 10: 4 (hand-pipelined cholesky_rows) or 6 (cholesky_rows_w, one panel per time
+// block).  6 measured between +2 % and -25 % at h = 10 depending on the build, -12 % at h = 5, -33 % at h = 20:
+// kept as an A/B option only.
+#ifndef RG_CHOL_W_H10
+#define RG_CHOL_W_H10 4
+#endif
 #ifndef RG_MIN_BLOCKS_H10
 #define RG_MIN_BLOCKS_H10 8
 #endif
 #ifndef RG_MIN_BLOCKS_H5
 #define RG_MIN_BLOCKS_H5 24
 #endif
+  static constexpr int CHOL_W = (H == 10) ? RG_CHOL_W_H10 : 4;
   static constexpr int MIN_BLOCKS = H <= 5 ? RG_MIN_BLOCKS_H5 : (H <= 10 ? RG_MIN_BLOCKS_H10 : 2);
 };
 
@@ -87,7 +94,7 @@ struct Smem {
   double avec[H * 6];              // W u, right-hand sides and Woodbury solutions
   double kvec[H * 6];              // K (W u)
   double rdiag[Cfg<H>::N6];
-  double blk44[16];                // updated 4x4 diagonal block of the current Cholesky panel
+  double blk44[36];                // updated diagonal block of the current Cholesky panel (4x4 or 6x6)
   double bang[4][9];               // A_leg = I_world^-1 [r_leg]x
   double k2ang[9];
   double k1[6];
@@ -320,6 +327,89 @@ __device__ __noinline__ void cholesky_rows(Smem<H>& sm, int j_begin) {
       }
     }
     RG_TOCL(31, N6 - 1);
+    __syncthreads();
+  }
+}
+
+// Generic W-wide panel variant of cholesky_rows (compiler-scheduled update loop, right-looking factorisation of the
+// W x W diagonal block in registers).  RG_CHOL_W = 6 matches the 6 x 6 time blocks of Psi: 10 panels instead of 15
+// at h = 10, and a partial refactorisation can restart at ANY time block (6 t_begin is always a panel boundary).
+template <int H, int W>
+__device__ __noinline__ void cholesky_rows_w(Smem<H>& sm, int j_begin) {
+  constexpr int N6 = Cfg<H>::N6;
+  static_assert(N6 % W == 0 && W * W <= 36, "panel width must divide 6h and fit the side buffer");
+  const int i = threadIdx.x;
+  const bool row_ok = i < N6;
+  double* row_i = sm.psi + prow(row_ok ? i : 0);
+  if (i == 0) sm.flag = 0;   // published by the first barrier below
+#pragma unroll 1
+  for (int j0 = j_begin; j0 < N6; j0 += W) {
+    double acc[W];
+    const bool in_play = row_ok && i >= j0;
+    if (in_play) {
+      const double* p[W];
+#pragma unroll
+      for (int c = 0; c < W; ++c) {
+        p[c] = sm.psi + prow(j0 + c);
+        acc[c] = (j0 + c <= i) ? row_i[j0 + c] : 0.0;
+      }
+#pragma unroll 2
+      for (int k = 0; k < j0; k += 2) {
+        const double2 a = ld2(row_i + k);
+#pragma unroll
+        for (int c = 0; c < W; ++c) {
+          const double2 b = ld2(p[c] + k);
+          acc[c] = fma(-a.x, b.x, acc[c]);
+          acc[c] = fma(-a.y, b.y, acc[c]);
+        }
+      }
+      if (i < j0 + W) {
+#pragma unroll
+        for (int c = 0; c < W; ++c) if (j0 + c <= i) sm.blk44[W * (i - j0) + c] = acc[c];
+      }
+    }
+    __syncthreads();
+    if (in_play) {
+      double a[W][W];
+#pragma unroll
+      for (int r = 0; r < W; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) a[r][c] = sm.blk44[W * r + c];
+      double rd[W];
+      bool bad = false;
+      const bool panel_row = i < j0 + W;
+#pragma unroll
+      for (int c = 0; c < W; ++c) {
+        double d = a[c][c];
+        if (!(d > 0.0)) { bad = true; d = 1e-300; }
+        rd[c] = rsqrt(d);
+#pragma unroll
+        for (int r = c + 1; r < W; ++r) a[r][c] *= rd[c];
+#pragma unroll
+        for (int r = c + 1; r < W; ++r)
+#pragma unroll
+          for (int cc = c + 1; cc <= r; ++cc) a[r][cc] = fma(-a[r][c], a[cc][c], a[r][cc]);
+        // the row below the block: x L_JJ^T = acc, eagerly (column c of the block is final here)
+        acc[c] *= rd[c];
+#pragma unroll
+        for (int r = c + 1; r < W; ++r) acc[r] = fma(-acc[c], a[r][c], acc[r]);
+      }
+      if (panel_row) {
+        const int r = i - j0;
+#pragma unroll
+        for (int rr = 0; rr < W; ++rr) {
+          if (rr == r) {
+#pragma unroll
+            for (int c = 0; c < rr; ++c) row_i[j0 + c] = a[rr][c];
+            sm.rdiag[i] = rd[rr];
+          }
+        }
+        if (bad && r == 0) sm.flag = 1;
+      } else {
+#pragma unroll
+        for (int c = 0; c < W; ++c) row_i[j0 + c] = acc[c];
+      }
+    }
     __syncthreads();
   }
 }
@@ -600,7 +690,8 @@ __device__ __forceinline__ void factor_psi(Smem<H>& sm, const RgMpcDev* __restri
   psi_build_rows<H>(sm, ws, t_begin);
   __syncthreads();
   RG_TOC(10);
-  cholesky_rows<H>(sm, 6 * t_begin);
+  if constexpr (Cfg<H>::CHOL_W == 4) cholesky_rows<H>(sm, 6 * t_begin);
+  else cholesky_rows_w<H, Cfg<H>::CHOL_W>(sm, 6 * t_begin);
   RG_TOC(11);
 }
 
@@ -1249,7 +1340,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
         if (active_blk && act != act_fact) tmin = (double)t_blk;
         if (!fact_valid) tmin = 0.0;
         block_reduce<C::NW>(dsum, dmx, tmin, sm.red);
-        if (tmin < (double)H) factor_psi<H>(sm, ws, blk, mproj, ((int)tmin) & ~1);
+        if (tmin < (double)H) factor_psi<H>(sm, ws, blk, mproj, C::CHOL_W == 4 ? (((int)tmin) & ~1) : (int)tmin);
         else if (tid == 0) sm.flag = 0;
         act_fact = act;
         fact_valid = true;
@@ -1487,7 +1578,8 @@ __global__ void __launch_bounds__(Cfg<H>::NT) chol_selftest_kernel(const double*
     for (int k = 0; k <= tid; ++k) sm.psi[prow(tid) + k] = a_dense[tid * N6 + k];
   }
   __syncthreads();
-  cholesky_rows<H>(sm, 0);
+  if constexpr (Cfg<H>::CHOL_W == 4) cholesky_rows<H>(sm, 0);
+  else cholesky_rows_w<H, Cfg<H>::CHOL_W>(sm, 0);
   if (tid < N6) sm.avec[tid] = rhs[tid];   // after the factorisation: avec / kvec are its scratch
   __syncthreads();
   if (tid < 32) tri_solve_warp0<H>(sm);
