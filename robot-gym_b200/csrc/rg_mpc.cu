@@ -79,6 +79,10 @@ struct Cfg {
 #ifndef RG_MIN_BLOCKS_H10
 #define RG_MIN_BLOCKS_H10 8
 #endif
+// the two heavy routines: one out-of-line copy each (default) or inlined at their call sites (A/B)
+#ifndef RG_HEAVY_INLINE
+#define RG_HEAVY_INLINE __noinline__
+#endif
 #ifndef RG_MIN_BLOCKS_H5
 #define RG_MIN_BLOCKS_H5 24
 #endif
@@ -205,7 +209,7 @@ __device__ __forceinline__ double quad_sum(double v) {   // sum over the 4 legs 
 // j_begin (a multiple of 4): columns before it already hold the factor and are kept -- a matrix that
 // changed only in rows/columns >= j_begin has the same leading factor columns (left-looking order).
 template <int H>
-__device__ __noinline__ void cholesky_rows(Smem<H>& sm, int j_begin) {
+__device__ RG_HEAVY_INLINE void cholesky_rows(Smem<H>& sm, int j_begin) {
   constexpr int N6 = Cfg<H>::N6;
   constexpr int HALF = Cfg<H>::NT / 2;
   // Helper threads (RG_CHOL_HELPERS): once the panel has moved past row HALF the lower half of the CTA owns
@@ -335,7 +339,7 @@ __device__ __noinline__ void cholesky_rows(Smem<H>& sm, int j_begin) {
 // W x W diagonal block in registers).  RG_CHOL_W = 6 matches the 6 x 6 time blocks of Psi: 10 panels instead of 15
 // at h = 10, and a partial refactorisation can restart at ANY time block (6 t_begin is always a panel boundary).
 template <int H, int W>
-__device__ __noinline__ void cholesky_rows_w(Smem<H>& sm, int j_begin) {
+__device__ RG_HEAVY_INLINE void cholesky_rows_w(Smem<H>& sm, int j_begin) {
   constexpr int N6 = Cfg<H>::N6;
   static_assert(N6 % W == 0 && W * W <= 36, "panel width must divide 6h and fit the side buffer");
   const int i = threadIdx.x;
@@ -423,7 +427,7 @@ __device__ __noinline__ void cholesky_rows_w(Smem<H>& sm, int j_begin) {
 // T(i) mod 16 is a permutation over the even and over the odd rows of 16 consecutive lanes, so the
 // per-column loads stay bank-conflict free with this ownership too.
 template <int H>
-__device__ __noinline__ void tri_solve_warp0(Smem<H>& sm) {
+__device__ RG_HEAVY_INLINE void tri_solve_warp0(Smem<H>& sm) {
   constexpr int N6 = Cfg<H>::N6;
   constexpr int RPL = Cfg<H>::RPL;
   constexpr int NL = N6 / RPL;
