@@ -13,9 +13,14 @@
 //    block-diagonal 3x3 part E = 2 alpha I + G^T D G:  only a 6h x 6h SPD matrix
 //    Psi = K^-1 + W E^-1 W^T is factorised (60 x 60 at h = 10 instead of 120 x 120).
 //  * K^-1 comes from a host-precomputed generalised eigen-decomposition of (c2, c1).
-//  * Mehrotra predictor-corrector interior point from a strictly feasible start to a loose
-//    tolerance, then an exact null-space active-set polish (the analogue of OSQP's polish),
-//    verified against primal feasibility and multiplier signs.
+//  * The solver: verified active-set rounds -- the equality-constrained QP on the
+//    guessed active rows is solved exactly in the per-block null space and the guess is checked
+//    against primal feasibility, multiplier signs and stationarity (the analogue of OSQP's polish);
+//    a verified round is the optimum.  They start cold (fz >= fz_min active in the last horizon
+//    step) or from the set the same env verified one control step earlier, and refactorise only the
+//    time blocks whose rows moved.  Problems on which the rounds cycle fall back to a Mehrotra
+//    predictor-corrector interior point from a strictly feasible start, which hands its active rows
+//    back to the rounds; an escalation ladder drives the interior point deeper when they do not verify.
 //
 // Thread roles inside a CTA (NT = 32 * ceil(6h / 32) threads):
 //   "block" threads  tid < 4h : own one (time step, leg) force triple with its 10 slacks and
