@@ -86,11 +86,10 @@ typedef struct rg_mpc_params {
   int32_t max_ipm_iters;       /* hard cap (40) */
   int32_t max_polish_rounds;   /* rounds per attempt (3); 0 disables the verified active-set rounds:
                                   the interior point alone leaves ~1e-3 relative in the alpha-directions */
-  int32_t cold_start_rounds;   /* active-set rounds tried from the unconstrained minimiser BEFORE the
-                                  interior point (5; it also stops as soon as the number of
-                                  rows that move stops shrinking); 0 = always run the interior point first */
-  int32_t cold_start_max_violations; /* give the cold start up at once when the unconstrained minimiser
-                                  violates more friction-cone rows than this (16 * horizon / 10) */
+  int32_t cold_start_rounds;   /* active-set rounds tried from the guessed / warm-started set BEFORE the interior
+                                  point (12); 0 = always run the interior point first */
+  int32_t cold_start_max_violations; /* > 0: hand over to the interior point at once when the first round finds
+                                  more violated friction-cone rows than this; 0 (default) = no limit */
 } rg_mpc_params;
 
 /* Fill `p` with the motion_imitation defaults for the given mass/inertia/height. */

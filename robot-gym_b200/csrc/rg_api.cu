@@ -181,8 +181,8 @@ extern "C" int rg_mpc_default_params(rg_mpc_params* p, double mass, const double
   p->ipm_tol = 1e-6;
   p->max_ipm_iters = 40;
   p->max_polish_rounds = 3;
-  p->cold_start_rounds = 5;
-  p->cold_start_max_violations = horizon > 0 ? (16 * horizon + 9) / 10 : 16;
+  p->cold_start_rounds = 12;
+  p->cold_start_max_violations = 0;   // 0 = no limit
   return RG_OK;
 }
 
@@ -232,7 +232,7 @@ extern "C" int rg_mpc_setup(const rg_mpc_params* p, void* workspace, size_t work
   h.max_polish_rounds = p->max_polish_rounds;
   // the cold start is the polish without an interior-point guess: it needs the polish enabled
   h.cold_start_rounds = (p->max_polish_rounds > 0 && p->cold_start_rounds > 0) ? p->cold_start_rounds : 0;
-  h.cold_start_max_violations = p->cold_start_max_violations > 0 ? p->cold_start_max_violations : 0;
+  h.cold_start_max_violations = p->cold_start_max_violations > 0 ? p->cold_start_max_violations : (1 << 30);
   h.inv_mass = 1.0 / p->mass;
   if (!inv3(p->inertia, h.inv_inertia)) { rg_set_error("inertia matrix is singular"); return RG_ERR_SINGULAR; }
   h.dt = p->dt;

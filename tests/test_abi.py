@@ -51,7 +51,7 @@ def test_default_params_follow_motion_imitation_defaults(rg_lib):
     assert list(p.friction_coeffs) == [0.45] * 4
     assert p.fz_max == pytest.approx(1900.0) and p.fz_min == pytest.approx(19.0)
     assert p.desired_body_height == 0.42
-    assert p.cold_start_rounds == 5 and p.cold_start_max_violations == 16 and p.max_polish_rounds == 3
+    assert p.cold_start_rounds == 12 and p.cold_start_max_violations == 0 and p.max_polish_rounds == 3
 
 
 def test_error_codes_and_messages(rg_lib):

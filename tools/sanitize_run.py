@@ -18,8 +18,8 @@ for h in (10, 5, 20):
     f, hf, info = rg.mpc_build_solve(ws, t(st.com_velocity_body), t(st.base_rpy), t(st.base_rpy_rate), t(st.planned_contacts), t(st.foot_positions_base), t(st.command), want_horizon=True)
     torch.cuda.synchronize()
     print("h", h, "ok", np.isfinite(f.cpu().numpy()).all(), info.cpu().numpy()[:, 2].min())
-# a pace schedule sends ~1/3 of the envs through the interior-point fallback (warm start, escalation ladder)
-pace = with_gait(GHOST, "pace")
+# a bound schedule sends ~15 % of the envs through the interior-point fallback (warm start, escalation ladder)
+pace = with_gait(GHOST, "bound")
 p = rg.default_mpc_params(ctrl.MPC_BODY_MASS, ctrl.MPC_BODY_INERTIA, ctrl.MPC_BODY_HEIGHT, 10)
 ws = rg.MpcWorkspace(p)
 st = synthetic.make_states(n, pace, seed=5)
@@ -27,7 +27,7 @@ t = lambda a: torch.from_numpy(a).cuda()
 f, hf, info = rg.mpc_build_solve(ws, t(st.com_velocity_body), t(st.base_rpy), t(st.base_rpy_rate), t(st.planned_contacts), t(st.foot_positions_base), t(st.command))
 torch.cuda.synchronize()
 inf = info.cpu().numpy()
-print("pace ok", np.isfinite(f.cpu().numpy()).all(), "interior-point envs", int((inf[:, 0] > 0).sum()), "of", n)
+print("bound ok", np.isfinite(f.cpu().numpy()).all(), "interior-point envs", int((inf[:, 0] > 0).sum()), "of", n)
 st = synthetic.make_states(n, GHOST, seed=3)
 robot = SyntheticRobotBatch(GHOST, st)
 ctl = BatchedMPCController(robot, robot.GetTimeSinceReset)
