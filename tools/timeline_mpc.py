@@ -35,13 +35,13 @@ def main():
     dur = end - start
     cold = (inf[:, 2] & 16) != 0
     print(f"n={n}: kernel span {end.max():.1f} us; CTA durations: cold mean {dur[cold].mean():.1f} p50 {np.median(dur[cold]):.1f} p99 {np.percentile(dur[cold], 99):.1f} max {dur[cold].max():.1f} us"
-          f" | interior-point envs ({(~cold).sum()}): mean {dur[~cold].mean():.1f} max {dur[~cold].max():.1f} us")
+          + (f" | interior-point envs ({(~cold).sum()}): mean {dur[~cold].mean():.1f} max {dur[~cold].max():.1f} us" if (~cold).any() else " | no interior-point envs"))
     order = np.argsort(end)[::-1][:12]
     print("   last CTAs to finish: (env, start us, end us, ipm iters, rounds, status)")
     for e in order: print(f"     {e:5d} {start[e]:8.1f} {end[e]:8.1f}  {inf[e,0]:2d} {inf[e,1]:2d} {inf[e,2]:3d}")
     for q in (0.25, 0.5, 0.75, 0.9, 0.99): print(f"   {int(q*100)} % of envs done by {np.quantile(end, q):.1f} us; last start {start.max():.1f} us")
     rounds = inf[:, 1]
-    for r in range(1, 10):
+    for r in range(1, 16):
         sel = cold & (rounds == r)
         if sel.any(): print(f"   cold, {r} rounds: {sel.sum():5d} envs, mean duration {dur[sel].mean():.1f} us")
 
