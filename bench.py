@@ -190,7 +190,28 @@ def run_gpu(args):
     ws = rg.MpcWorkspace(params, device=dev)
 
     host_names = ("com_velocity_body", "base_rpy", "base_rpy_rate", "planned_contacts", "foot_positions_base", "command")
-    host = {k: torch.from_numpy(np.ascontiguousarray(getattr(states, k))).pin_memory() for k in host_names}
+    # The six input arrays live back to back in ONE pinned host allocation (and one device allocation for the
+    # e2e arm), 256-byte aligned: the public API still receives six tensors (views), but a step needs one
+    # host->device copy instead of six.
+    arrays = {k: np.ascontiguousarray(getattr(states, k)) for k in host_names}
+    offsets, total_bytes = {}, 0
+    for k, a in arrays.items():
+        offsets[k] = total_bytes
+        total_bytes += (a.nbytes + 255) // 256 * 256
+    host_pack = torch.empty(max(total_bytes, 256), dtype=torch.uint8).pin_memory()
+    e2e_pack = torch.empty(max(total_bytes, 256), dtype=torch.uint8, device=dev)
+
+    def views(pack):
+        out = {}
+        for k, a in arrays.items():
+            flat = pack[offsets[k]:offsets[k] + a.nbytes]
+            out[k] = flat.view(torch.from_numpy(a).dtype).view(a.shape)
+        return out
+
+    host = views(host_pack)
+    for k, a in arrays.items():
+        host[k].copy_(torch.from_numpy(a))
+    e2e_in = views(e2e_pack)
     dev_in = {k: v.to(dev) for k, v in host.items()}
     forces = torch.empty((n, 12), dtype=torch.float32, device=dev)
     info = torch.empty((n, 4), dtype=torch.int32, device=dev)
@@ -245,9 +266,9 @@ def run_gpu(args):
 
     # ---- e2e: host buffers in, host forces out, copies inside the timed region
     def e2e_step():
-        inputs = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        solve(inputs)
-        forces_host.copy_(forces, non_blocking=True)
+        e2e_pack.copy_(host_pack, non_blocking=True)        # pinned host -> device, this step's inputs
+        solve(e2e_in)
+        forces_host.copy_(forces, non_blocking=True)        # device -> pinned host, this step's result
     for _ in range(3):
         e2e_step()
     barrier()
@@ -269,7 +290,7 @@ def run_gpu(args):
         solve(dev_in)
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
-    h2d = sum(v.numel() * v.element_size() for v in host.values()) * world
+    h2d = sum(v.numel() * v.element_size() for v in host.values()) * world      # payload (the packed copy adds < 2 KB of alignment padding)
     d2h = forces_host.numel() * forces_host.element_size() * world
 
     # ---- solver statistics (whole job)
