@@ -129,6 +129,8 @@ __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_ca
 __device__ __forceinline__ int prow(int i) { return i * (i + 1) / 2; }
 __device__ __forceinline__ double2 ld2(const double* p) { return make_double2(p[0], p[1]); }
 #endif
+// 128-bit load of two consecutive doubles; the caller guarantees 16-byte alignment
+__device__ __forceinline__ double2 ld2v(const double* p) { return *reinterpret_cast<const double2*>(p); }
 
 __device__ __forceinline__ double c1f(int h, int j, int k) { return (double)(h - (j > k ? j : k)); }
 
@@ -158,11 +160,9 @@ __device__ __forceinline__ double c1f(int h, int j, int k) { return (double)(h -
 #ifndef RG_IPM_SLOW_ITERS
 #define RG_IPM_SLOW_ITERS 5
 #endif
-// Cholesky: idle lower-half threads take half of each late panel's dot products (see cholesky_rows).
-// OFF: it shortens a factorisation alone on an SM but measured 3-6 % slower with 8 CTAs per SM (the
-// launch is throughput-bound there; a warp parked at a barrier costs nothing, a helper warp does).
-#ifndef RG_CHOL_HELPERS
-#define RG_CHOL_HELPERS 0
+// Cholesky update loop: 128-bit broadcast loads of the panel rows (see cholesky_rows)
+#ifndef RG_CHOL_LDS128
+#define RG_CHOL_LDS128 1
 #endif
 // cold start: fz >= fz_min is guessed active in the last RG_COLD_GUESS_LAST steps of the horizon (0 = empty set)
 #ifndef RG_COLD_GUESS_LAST
@@ -224,14 +224,6 @@ __device__ __forceinline__ double quad_sum(double v) {   // sum over the 4 legs 
 template <int H>
 __device__ RG_HEAVY_INLINE void cholesky_rows(Smem<H>& sm, int j_begin) {
   constexpr int N6 = Cfg<H>::N6;
-  constexpr int HALF = Cfg<H>::NT / 2;
-  // Helper threads (RG_CHOL_HELPERS): once the panel has moved past row HALF the lower half of the CTA owns
-  // no row in play, so thread t < HALF takes the FIRST half of the k-range of row HALF + t and the row's own
-  // thread the second half.  Both run the same uniform loop (same trip count, uniform panel-row bases) and
-  // differ only in a per-thread start offset.  Partial sums travel through sm.avec / sm.kvec, which hold
-  // nothing live during a factorisation.
-  constexpr bool kHelpers = RG_CHOL_HELPERS && Cfg<H>::NW >= 2 && 4 * (N6 - HALF) <= 12 * H;
-  double* part = sm.avec;
   const int i = threadIdx.x;
   const bool row_ok = i < N6;
   double* row_i = sm.psi + prow(row_ok ? i : 0);
@@ -243,38 +235,52 @@ __device__ RG_HEAVY_INLINE void cholesky_rows(Smem<H>& sm, int j_begin) {
     const int w = N6 - j0 < 4 ? N6 - j0 : 4;          // panel width (the last panel of N6 = 30 has 2 columns)
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     const bool in_play = row_ok && i >= j0;
-    const bool helper_mode = kHelpers && j0 >= HALF;  // uniform
-    const bool is_helper = helper_mode && i < HALF;
-    const int wrow = is_helper ? i + HALF : i;        // the row this thread accumulates for
-    if (is_helper ? (wrow >= j0 && wrow < N6) : in_play) {
-      const int ng = helper_mode ? (j0 >> 2) : (j0 >> 1);   // pair-steps per thread (uniform); j0 % 4 == 0
-      const int off = (helper_mode && !is_helper) ? (j0 >> 1) : 0;   // the row thread starts at column j0 / 2
-      const double* r2 = sm.psi + prow(wrow) + off;
-      const double* p0 = sm.psi + prow(j0) + off;
-      const double* p1 = sm.psi + prow(j0 + (w > 1 ? 1 : 0)) + off;
-      const double* p2 = sm.psi + prow(j0 + (w > 2 ? 2 : 0)) + off;
-      const double* p3 = sm.psi + prow(j0 + (w > 3 ? 3 : 0)) + off;
-      if (!is_helper) {
+    if (in_play) {
+      const double* r2 = row_i;
+      const double* p0 = sm.psi + prow(j0);
+      const double* p1 = sm.psi + prow(j0 + (w > 1 ? 1 : 0));
+      const double* p2 = sm.psi + prow(j0 + (w > 2 ? 2 : 0));
+      const double* p3 = sm.psi + prow(j0 + (w > 3 ? 3 : 0));
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[c] = (c < w && j0 + c <= i) ? row_i[j0 + c] : 0.0;
-      }
-      // software-pipelined dot products: the loads of step g+1 are in flight while step g's
-      // eight FMAs retire (the loop is latency-bound on shared memory otherwise: 2 warps per CTA)
-      double2 a = ld2(r2), b0 = ld2(p0), b1 = ld2(p1), b2 = ld2(p2), b3 = ld2(p3);
+      for (int c = 0; c < 4; ++c) acc[c] = (c < w && j0 + c <= i) ? row_i[j0 + c] : 0.0;
+      const int ng = j0 >> 1;                          // pairs of columns already factored (j0 % 4 == 0)
+      if (w == 4 && RG_CHOL_LDS128) {
+        // 128-bit broadcast loads of the panel rows.  T(r) = r(r+1)/2 is even for r = 0, 3 (mod 4) and odd for
+        // r = 1, 2 (mod 4): rows j0 and j0+3 are 16-byte aligned at even k, rows j0+1 and j0+2 at odd k.  The
+        // latter two are read as the pairs (2g+1, 2g+2) and consumed with a one-element lag.  All loads of step
+        // g+1 are in flight while step g's eight FMAs retire; the last prefetch over-reads by <= 2 doubles
+        // (still inside Psi / its slack, values unused).
+        double2 a = ld2(r2);
+        double2 b0 = ld2v(p0), b3 = ld2v(p3);
+        double b1x = p1[0], b2x = p2[0];
+        double2 q1 = ld2v(p1 + 1), q2 = ld2v(p2 + 1);
 #pragma unroll 2
-      for (int g = 0; g < ng; ++g) {
-        const int gn = g + 1 < ng ? g + 1 : g;
-        const double2 an = ld2(r2 + 2 * gn), c0 = ld2(p0 + 2 * gn), c1 = ld2(p1 + 2 * gn), c2 = ld2(p2 + 2 * gn), c3 = ld2(p3 + 2 * gn);
-        acc[0] = fma(-a.x, b0.x, acc[0]); acc[1] = fma(-a.x, b1.x, acc[1]);
-        acc[2] = fma(-a.x, b2.x, acc[2]); acc[3] = fma(-a.x, b3.x, acc[3]);
-        acc[0] = fma(-a.y, b0.y, acc[0]); acc[1] = fma(-a.y, b1.y, acc[1]);
-        acc[2] = fma(-a.y, b2.y, acc[2]); acc[3] = fma(-a.y, b3.y, acc[3]);
-        a = an; b0 = c0; b1 = c1; b2 = c2; b3 = c3;
+        for (int g = 0; g < ng; ++g) {
+          const double2 an = ld2(r2 + 2 * g + 2);
+          const double2 c0 = ld2v(p0 + 2 * g + 2), c3 = ld2v(p3 + 2 * g + 2);
+          const double2 n1 = ld2v(p1 + 2 * g + 3), n2 = ld2v(p2 + 2 * g + 3);
+          acc[0] = fma(-a.x, b0.x, acc[0]); acc[1] = fma(-a.x, b1x, acc[1]);
+          acc[2] = fma(-a.x, b2x, acc[2]);  acc[3] = fma(-a.x, b3.x, acc[3]);
+          acc[0] = fma(-a.y, b0.y, acc[0]); acc[1] = fma(-a.y, q1.x, acc[1]);
+          acc[2] = fma(-a.y, q2.x, acc[2]); acc[3] = fma(-a.y, b3.y, acc[3]);
+          b1x = q1.y; b2x = q2.y;
+          a = an; b0 = c0; b3 = c3; q1 = n1; q2 = n2;
+        }
+      } else {
+        // scalar pair loads, software-pipelined one stage ahead
+        double2 a = ld2(r2), b0 = ld2(p0), b1 = ld2(p1), b2 = ld2(p2), b3 = ld2(p3);
+#pragma unroll 2
+        for (int g = 0; g < ng; ++g) {
+          const int gn = g + 1 < ng ? g + 1 : g;
+          const double2 an = ld2(r2 + 2 * gn), c0 = ld2(p0 + 2 * gn), c1 = ld2(p1 + 2 * gn), c2 = ld2(p2 + 2 * gn), c3 = ld2(p3 + 2 * gn);
+          acc[0] = fma(-a.x, b0.x, acc[0]); acc[1] = fma(-a.x, b1.x, acc[1]);
+          acc[2] = fma(-a.x, b2.x, acc[2]); acc[3] = fma(-a.x, b3.x, acc[3]);
+          acc[0] = fma(-a.y, b0.y, acc[0]); acc[1] = fma(-a.y, b1.y, acc[1]);
+          acc[2] = fma(-a.y, b2.y, acc[2]); acc[3] = fma(-a.y, b3.y, acc[3]);
+          a = an; b0 = c0; b1 = c1; b2 = c2; b3 = c3;
+        }
       }
-      if (is_helper) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) part[4 * i + c] = acc[c];
-      } else if (i < j0 + w) {                         // a panel row: publish the updated entries A'[i][j0..i]
+      if (i < j0 + w) {                                // a panel row: publish the updated entries A'[i][j0..i]
         // into the side buffer, NOT into Psi: phase 2 overwrites the panel rows of Psi with the factor
         // while other warps may still be reading the block (that was a cross-warp race)
 #pragma unroll
@@ -291,14 +297,6 @@ __device__ RG_HEAVY_INLINE void cholesky_rows(Smem<H>& sm, int j_begin) {
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c <= r; ++c) a[r][c] = (r < w) ? sm.blk44[4 * r + c] : (r == c ? 1.0 : 0.0);
-      if (helper_mode) {                               // add the helpers' halves (block rows and own row)
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c <= r; ++c) if (r < w) a[r][c] += part[4 * (j0 + r - HALF) + c];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[c] += part[4 * (i - HALF) + c];
-      }
       // factor: l[r][c] for c < r, inverse diagonal in rd[r]
       double rd[4];
       bool bad = false;
