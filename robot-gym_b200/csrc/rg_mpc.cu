@@ -103,7 +103,7 @@ struct Smem {
   double avec[H * 6];              // W u, right-hand sides and Woodbury solutions
   double kvec[H * 6];              // K (W u)
   double rdiag[Cfg<H>::N6];
-  double blk44[36];                // updated diagonal block of the current Cholesky panel (4x4 or 6x6)
+  __align__(16) double blk44[36];  // updated diagonal block of the current Cholesky panel (4x4 or 6x6)
   double bang[4][9];               // A_leg = I_world^-1 [r_leg]x
   double k2ang[9];
   double k1[6];
@@ -293,10 +293,19 @@ __device__ RG_HEAVY_INLINE void cholesky_rows(Smem<H>& sm, int j_begin) {
     if (in_play) {
       // 4x4 diagonal block A' (lower triangle), broadcast loads; entries beyond the panel width read as identity
       double a[4][4];
+      {
+        // six 128-bit broadcast loads instead of ten 64-bit ones (entries above the diagonal are stale, unused)
+        const double2 r0 = ld2v(sm.blk44), r1 = ld2v(sm.blk44 + 4), r2a = ld2v(sm.blk44 + 8), r2b = ld2v(sm.blk44 + 10),
+                      r3a = ld2v(sm.blk44 + 12), r3b = ld2v(sm.blk44 + 14);
+        a[0][0] = r0.x;
+        a[1][0] = r1.x; a[1][1] = r1.y;
+        a[2][0] = r2a.x; a[2][1] = r2a.y; a[2][2] = r2b.x;
+        a[3][0] = r3a.x; a[3][1] = r3a.y; a[3][2] = r3b.x; a[3][3] = r3b.y;
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c <= r; ++c) a[r][c] = (r < w) ? sm.blk44[4 * r + c] : (r == c ? 1.0 : 0.0);
+          for (int c = 0; c <= r; ++c) if (r >= w) a[r][c] = (r == c ? 1.0 : 0.0);
+      }
       // factor: l[r][c] for c < r, inverse diagonal in rd[r]
       double rd[4];
       bool bad = false;
