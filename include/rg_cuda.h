@@ -60,7 +60,9 @@ enum {
   RG_STATUS_IPM_CONVERGED = 2,   /* interior-point residual below tolerance */
   RG_STATUS_NO_STANCE = 4,       /* no foot in contact: all forces are zero by the bounds */
   RG_STATUS_NUMERIC = 8,         /* non-positive pivot met (result is the last good iterate) */
-  RG_STATUS_ACTIVE_SET_ONLY = 16 /* the cold-start active-set iteration verified; no interior point ran */
+  RG_STATUS_ACTIVE_SET_ONLY = 16,/* the cold-start active-set iteration verified; no interior point ran */
+  RG_STATUS_BAD_WORKSPACE = 32   /* the workspace on the device is not the one rg_mpc_setup prepared for this horizon
+                                    (freed / overwritten without rg_mpc_release): forces are zero, nothing was solved */
 };
 
 /* ---- ConvexMpc constructor arguments + the constants compiled into mpc_osqp ------------
@@ -90,17 +92,25 @@ typedef struct rg_mpc_params {
                                   point (12); 0 = always run the interior point first */
   int32_t cold_start_max_violations; /* > 0: hand over to the interior point at once when the first round finds
                                   more violated friction-cone rows than this; 0 (default) = no limit */
+  int32_t two_kernel_solve;    /* 1 (default): a lean active-set-only kernel solves every env and queues the ones its
+                                  rounds cannot verify; the complete solver (interior point, escalation) then runs on
+                                  that list only.  0: one kernel with the complete solver for every env.  Same
+                                  results either way; needs cold_start_rounds > 0 and a workspace sized for n_env. */
+  int32_t reserved_;
 } rg_mpc_params;
 
 /* Fill `p` with the motion_imitation defaults for the given mass/inertia/height. */
 int rg_mpc_default_params(rg_mpc_params* p_host, double mass, const double* inertia9_host,
                           double desired_body_height, int horizon);
 
-/* Bytes of device workspace rg_mpc_setup needs (tables only; independent of n_env). */
+/* Bytes of device workspace rg_mpc_setup needs: parameter block + horizon tables, plus the fallback queue of the
+ * two-kernel solve for batches of up to n_env envs (4 bytes per env).  A solve of more envs than the workspace was
+ * sized for still works: it uses the single complete kernel. */
 int rg_workspace_bytes(int n_env, int horizon, int num_legs, size_t* bytes_host);
 
 /* One-time: validates params, computes the horizon tables on the host and uploads them plus
- * the parameters into `workspace`.  Synchronises `stream`. */
+ * the parameters into `workspace` (256-byte aligned).  Synchronises `stream`.  A workspace serves one solve at a
+ * time: concurrent solves on different streams need a workspace each (the queue lives in it). */
 int rg_mpc_setup(const rg_mpc_params* p_host, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Forget a workspace prepared by rg_mpc_setup (call before freeing or reusing its memory). */
@@ -111,9 +121,11 @@ int rg_mpc_release(const void* workspace);
  * as called by TorqueStanceLegController.get_action (mpc_controller.py:47-56,105).
  * One QP per env: builds the condensed centroidal QP over the horizon and solves it.
  *   com_velocity_body  [N,3]  f32   state estimator body-frame COM velocity
- *   base_rpy           [N,3]  f32   roll, pitch, yaw (the python wrapper zeroes yaw)
+ *   base_rpy           [N,3]  f32   roll, pitch, yaw.  The yaw is used AS GIVEN: TorqueStanceLegController passes a
+ *                                   yaw-aligned attitude (yaw = 0); rg_control_step zeroes it itself, a direct caller
+ *                                   of this entry point (or of robot_gym.cuda.mpc_build_solve) must do so too
  *   base_rpy_rate      [N,3]  f32   Robot.GetBaseRollPitchYawRate (robot.py:205-213)
- *   foot_contact_state [N,4]  u8    1 = planned stance (held over the horizon)
+ *   foot_contact_state [N,4]  u8    1 = planned stance (held over the horizon); 4-byte aligned
  *   foot_positions_base[N,12] f32   Robot.GetFootPositionsInBaseFrame (robot.py:389-397)
  *   command            [N,3]  f32   desired (vx, vy, wz) incl. per-robot offsets
  *   com_height         [N]    f32   or NULL -> EstimateCoMHeightSimple from the stance feet
@@ -142,6 +154,30 @@ int rg_mpc_build_solve_warm(const void* workspace, int n_env, const float* com_v
                             const uint8_t* foot_contact_state, const float* foot_positions_base,
                             const float* command, const float* com_height, float* contact_forces,
                             float* horizon_forces, int32_t* solve_info, uint16_t* active_set_io, void* stream);
+
+/* The same solve with every argument in one struct (the two entry points above forward to it), plus two things
+ * they do not expose:
+ *   zero_yaw            != 0: the solve uses yaw = 0 whatever base_rpy[:,2] holds -- what TorqueStanceLegController
+ *                       does before it calls compute_contact_forces ("yaw aligned world frame")
+ *   horizon_forces_f64  [N,h,12] f64 OUT or NULL: the full solution in the precision it was computed in (the
+ *                       reference's solver returns doubles; the f32 outputs round it to ~1e-7 relative). */
+typedef struct rg_mpc_io {
+  const float* com_velocity_body;      /* [N,3]  */
+  const float* base_rpy;               /* [N,3]  */
+  const float* base_rpy_rate;          /* [N,3]  */
+  const uint8_t* foot_contact_state;   /* [N,4]  4-byte aligned */
+  const float* foot_positions_base;    /* [N,12] */
+  const float* command;                /* [N,3]  */
+  const float* com_height;             /* [N] or NULL */
+  float* contact_forces;               /* [N,12] OUT */
+  float* horizon_forces;               /* [N,h,12] OUT or NULL */
+  int32_t* solve_info;                 /* [N,4] OUT or NULL */
+  uint16_t* active_set_io;             /* [N,4h] in/out or NULL */
+  double* horizon_forces_f64;          /* [N,h,12] OUT or NULL */
+  int32_t zero_yaw;
+  int32_t reserved_;
+} rg_mpc_io;
+int rg_mpc_build_solve_io(const void* workspace, int n_env, const rg_mpc_io* io_host, void* stream);
 
 /* ---- robot model: leg chains + gait + gains ------------------------------------------------
  * Replaces the per-robot python constants the third-party stack reads through the robot

@@ -7,9 +7,9 @@
  * reference's own dense formulation: A/B matrices, Pade scaling-and-squaring matrix exponential of
  * [[A,B],[0,0]]*dt (what Eigen's MatrixBase::exp() does), stacked A_qp / B_qp, dense
  * P = 2 (B_qp^T L B_qp + alpha I), q = 2 B_qp^T L (A_qp x0 - x_ref), 5 pyramid rows per foot per step.
- * The QP is solved by a dense Mehrotra predictor-corrector interior point (the reference uses OSQP
- * ADMM + polish; OSQP is not available offline -- both converge to the unique optimum of the
- * strictly convex QP).  Swing feet (0 <= C f <= 0) are eliminated before the solve.
+ * The QP is solved by a dense Mehrotra predictor-corrector interior point followed by an exact
+ * active-set polish (the reference uses OSQP ADMM + polish; OSQP is not available offline -- both
+ * converge to the unique optimum of the strictly convex QP).  Swing feet (0 <= C f <= 0) are eliminated before the solve.
  *
  * Roles: (1) fast checker for the 4096-env GPU parity test, pinned against oracle/convex_mpc.py;
  * (2) the CPU baseline bench.py times ("port", one env per OpenMP thread iteration).
@@ -415,6 +415,82 @@ int rgo_compute_contact_forces(const rgo_params* p, const double* com_vel, const
     step = fmin(1.0, 0.99 * step);
     for (int a = 0; a < n; ++a) x[a] += step * dx[a];
     for (int j = 0; j < m; ++j) { s[j] += step * ds[j]; lam[j] += step * dl[j]; }
+  }
+  /* Active-set polish (the counterpart of OSQP's polish and of oracle/convex_mpc.py's refinement): solve the
+   * equality-constrained QP on the rows the interior point marks active exactly,
+   *     x = x_unc - Y y,   Y = P^-1 C_a^T,   (C_a Y) y = C_a x_unc - b_a,
+   * add violated rows, drop rows whose multiplier has the wrong sign, repeat.  Accepted only when a round
+   * changes nothing (a KKT point of a strictly convex QP = the optimum); otherwise the interior-point
+   * iterate stands.  phi / dxa / dx / rhs / wv are free here and reused as scratch. */
+  {
+    int* side = (int*)malloc(sizeof(int) * (size_t)(5 * nblk));          /* +1 upper, -1 lower, 0 free */
+    int* rows = (int*)malloc(sizeof(int) * (size_t)(5 * nblk));
+    double* lfac = phi;                                                    /* Cholesky factor of P */
+    double* xunc = dxa;
+    double* xp = dx;
+    memcpy(lfac, pm, sizeof(double) * (size_t)n * n);
+    int ok = cholesky(lfac, n) == 0;
+    if (ok) {
+      for (int a = 0; a < n; ++a) xunc[a] = -qv[a];
+      chol_solve(lfac, xunc, n);
+      for (int b = 0; b < nblk; ++b)
+        for (int r = 0; r < 5; ++r) {
+          const double c = grow[r][0] * xbest[3 * b] + grow[r][1] * xbest[3 * b + 1] + grow[r][2] * xbest[3 * b + 2];
+          const double span_hi = fmax(1.0, fabs(hup[r])), span_lo = fmax(1.0, fabs(lo[r]));
+          side[5 * b + r] = 0;
+          if (lam[10 * b + r] > s[10 * b + r] && hup[r] - c < 1e-5 * span_hi) side[5 * b + r] = 1;
+          if (lam[10 * b + 5 + r] > s[10 * b + 5 + r] && c - lo[r] < 1e-5 * fmax(span_hi, span_lo)) side[5 * b + r] = -1;
+        }
+    }
+    const double feas_tol = 1e-11 * fmax(1.0, big_u);
+    for (int round = 0; ok && round < 20; ++round) {
+      int ma = 0;
+      for (int j = 0; j < 5 * nblk; ++j) if (side[j]) rows[ma++] = j;
+      double* ymat = (double*)malloc(sizeof(double) * (size_t)(ma > 0 ? ma : 1) * n);      /* rows of Y^T */
+      double* smat = (double*)malloc(sizeof(double) * (size_t)(ma > 0 ? ma : 1) * (ma > 0 ? ma : 1));
+      double* yv = (double*)malloc(sizeof(double) * (size_t)(ma > 0 ? ma : 1));
+      for (int i = 0; i < ma; ++i) {
+        const int b = rows[i] / 5, r = rows[i] % 5;
+        double* col = ymat + (size_t)i * n;
+        memset(col, 0, sizeof(double) * n);
+        for (int d = 0; d < 3; ++d) col[3 * b + d] = grow[r][d];
+        chol_solve(lfac, col, n);
+      }
+      for (int i = 0; i < ma; ++i) {
+        const int b = rows[i] / 5, r = rows[i] % 5;
+        for (int j = 0; j < ma; ++j) {
+          const double* col = ymat + (size_t)j * n;
+          smat[(size_t)i * ma + j] = grow[r][0] * col[3 * b] + grow[r][1] * col[3 * b + 1] + grow[r][2] * col[3 * b + 2];
+        }
+        const double target = side[rows[i]] > 0 ? hup[r] : lo[r];
+        yv[i] = grow[r][0] * xunc[3 * b] + grow[r][1] * xunc[3 * b + 1] + grow[r][2] * xunc[3 * b + 2] - target;
+      }
+      if (ma > 0) {
+        if (cholesky(smat, ma) != 0) { ok = 0; free(ymat); free(smat); free(yv); break; }   /* dependent rows: keep the IPM point */
+        chol_solve(smat, yv, ma);
+      }
+      memcpy(xp, xunc, sizeof(double) * n);
+      for (int i = 0; i < ma; ++i) {
+        const double* col = ymat + (size_t)i * n;
+        for (int a = 0; a < n; ++a) xp[a] -= yv[i] * col[a];
+      }
+      int changed = 0;
+      double ymax = 1.0;
+      for (int i = 0; i < ma; ++i) if (fabs(yv[i]) > ymax) ymax = fabs(yv[i]);
+      for (int b = 0; b < nblk; ++b)
+        for (int r = 0; r < 5; ++r) {
+          if (side[5 * b + r]) continue;
+          const double c = grow[r][0] * xp[3 * b] + grow[r][1] * xp[3 * b + 1] + grow[r][2] * xp[3 * b + 2];
+          if (c - hup[r] > feas_tol) { side[5 * b + r] = 1; changed = 1; }
+          else if (lo[r] - c > feas_tol) { side[5 * b + r] = -1; changed = 1; }
+        }
+      for (int i = 0; i < ma; ++i)
+        if (side[rows[i]] * yv[i] < -1e-12 * ymax) { side[rows[i]] = 0; changed = 1; }
+      free(ymat); free(smat); free(yv);
+      if (!changed) { memcpy(xbest, xp, sizeof(double) * n); break; }
+      if (round == 19) ok = 0;
+    }
+    free(side); free(rows);
   }
   for (int a = 0; a < n; ++a) out[idx[a]] = -xbest[a];
   (void)rhs;

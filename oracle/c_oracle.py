@@ -42,6 +42,10 @@ def load():
         lib.rgo_batch.restype = ctypes.c_long
         lib.rgo_batch.argtypes = [ctypes.POINTER(RgoParams), ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_double] + \
                                  [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        lib.rgo_compute_contact_forces.restype = ctypes.c_int
+        lib.rgo_compute_contact_forces.argtypes = [ctypes.POINTER(RgoParams)] + [ctypes.c_void_p] * 12
+        lib.rgo_scratch_doubles.restype = ctypes.c_size_t
+        lib.rgo_scratch_doubles.argtypes = [ctypes.c_int, ctypes.c_int]
         _lib = lib
     return _lib
 
@@ -75,3 +79,24 @@ def solve_batch(mpc_params, states, desired_height, n_threads=1, want_horizon=Fa
                           out.ctypes.data_as(ctypes.c_void_p),
                           hout.ctypes.data_as(ctypes.c_void_p) if hout is not None else None, int(n_threads))
     return out, hout, int(iters)
+
+
+def compute_contact_forces(params, com_velocity, rpy, angular_velocity, contacts, foot_positions_base,
+                           desired_com_position, desired_com_velocity, desired_rpy, desired_angular_velocity,
+                           com_position=None):
+    """One env through the C port, float64 in and out: same signature and return value (the NEGATED solution,
+    3*k*h doubles) as ``oracle.convex_mpc.compute_contact_forces``, about 100x faster.  Lets the restated
+    LocomotionController (oracle/locomotion.py) be stepped over hundreds of envs in a test."""
+    lib = load()
+    p = params_from(params)
+    d = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    cv, r3, w3, ft = d(com_velocity), d(rpy), d(angular_velocity), d(foot_positions_base).reshape(-1)
+    ct = np.ascontiguousarray(np.asarray(contacts).astype(np.int32))
+    dp, dv, dr, dw = d(desired_com_position), d(desired_com_velocity), d(desired_rpy), d(desired_angular_velocity)
+    cp = d(com_position) if com_position is not None and len(com_position) == 3 else None
+    out = np.zeros(3 * params.num_legs * params.horizon, dtype=np.float64)
+    scratch = np.zeros(int(lib.rgo_scratch_doubles(params.horizon, params.num_legs)), dtype=np.float64)
+    lib.rgo_compute_contact_forces(ctypes.byref(p), ptr(cv), ptr(r3), ptr(w3), ptr(ct), ptr(ft), ptr(dp), ptr(dv), ptr(dr),
+                                   ptr(dw), ptr(cp) if cp is not None else None, ptr(out), ptr(scratch))
+    return out

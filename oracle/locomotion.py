@@ -290,7 +290,10 @@ class TorqueStanceLegController:
     def __init__(self, robot, gait_generator, state_estimator, desired_speed=(0, 0), desired_twisting_speed=0,
                  desired_body_height=0.45, body_mass=220 / 9.8,
                  body_inertia=(0.07335, 0, 0, 0, 0.25068, 0, 0, 0, 0.25447), num_legs=4,
-                 friction_coeffs=(0.45, 0.45, 0.45, 0.45), mpc_params=None):
+                 friction_coeffs=(0.45, 0.45, 0.45, 0.45), mpc_params=None, mpc_solver=None):
+        # mpc_solver: callable with the signature of convex_mpc.compute_contact_forces (default) -- the tests that
+        # step hundreds of envs pass oracle.c_oracle.compute_contact_forces, the same QP solved by the C port
+        self._mpc_solver = mpc_solver or convex_mpc.compute_contact_forces
         self._robot = robot
         self._gait_generator = gait_generator
         self._state_estimator = state_estimator
@@ -320,7 +323,7 @@ class TorqueStanceLegController:
             dtype=np.int32)
         com_roll_pitch_yaw = np.array(self._robot.GetBaseRollPitchYaw(), dtype=np.float64)
         com_roll_pitch_yaw[2] = 0
-        predicted_contact_forces = convex_mpc.compute_contact_forces(
+        predicted_contact_forces = self._mpc_solver(
             self._params,
             np.asarray(self._state_estimator.com_velocity_body_frame, dtype=np.float64),
             com_roll_pitch_yaw,
@@ -399,7 +402,7 @@ class LocomotionController:
         return np.array(action, dtype=np.float32)
 
 
-def build_mpc_controller(robot, clock, constants, mpc_params=None):
+def build_mpc_controller(robot, clock, constants, mpc_params=None, mpc_solver=None):
     """``MPCController._setup_controller`` (robot_gym/controllers/mpc/mpc_controller.py:28-66)."""
     gait = OpenloopGaitGenerator(robot, stance_duration=constants.STANCE_DURATION_SECONDS,
                                  duty_factor=constants.DUTY_FACTOR,
@@ -410,7 +413,7 @@ def build_mpc_controller(robot, clock, constants, mpc_params=None):
                                    desired_height=constants.MPC_BODY_HEIGHT, foot_clearance=0.01)
     stc = TorqueStanceLegController(robot, gait, est, desired_speed=(0.0, 0.0), desired_twisting_speed=0.0,
                                     desired_body_height=constants.MPC_BODY_HEIGHT, body_mass=constants.MPC_BODY_MASS,
-                                    body_inertia=constants.MPC_BODY_INERTIA, mpc_params=mpc_params)
+                                    body_inertia=constants.MPC_BODY_INERTIA, mpc_params=mpc_params, mpc_solver=mpc_solver)
     return LocomotionController(robot, gait, est, sw, stc, clock)
 
 

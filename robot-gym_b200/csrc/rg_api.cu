@@ -15,24 +15,21 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 std::mutex g_ws_mutex;
-std::unordered_map<const void*, int> g_ws_horizon;   // prepared MPC workspaces -> horizon
+std::unordered_map<const void*, RgMpcHostInfo> g_ws_info;   // workspaces prepared by rg_mpc_setup in this process
 }  // namespace
 
-int rg_mpc_workspace_horizon(const void* workspace, int* horizon) {
-  {
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
-    auto it = g_ws_horizon.find(workspace);
-    if (it != g_ws_horizon.end()) { *horizon = it->second; return RG_OK; }
-  }
-  // not prepared through this process' rg_mpc_setup (e.g. a copied workspace): read the header
-  RgMpcDev hdr;
-  int rc = rg_check_cuda(cudaMemcpy(&hdr, workspace, offsetof(RgMpcDev, inv_mass), cudaMemcpyDeviceToHost),
-                         "MPC workspace header read");
-  if (rc != RG_OK) return rc;
-  if (hdr.magic != RG_WS_MAGIC_MPC) { rg_set_error("workspace was not prepared by rg_mpc_setup"); return RG_ERR_WORKSPACE; }
+// Host-side record of a prepared workspace.  The launch path never touches the device for it (no synchronising
+// header read: that would break stream ordering and CUDA-graph capture); a workspace this process did not prepare
+// is rejected, and the kernels re-check magic and horizon on the device, so a stale record (memory freed and
+// reused without rg_mpc_release) yields RG_STATUS_BAD_WORKSPACE instead of an out-of-bounds access.
+int rg_mpc_workspace_info(const void* workspace, RgMpcHostInfo* info) {
   std::lock_guard<std::mutex> lock(g_ws_mutex);
-  g_ws_horizon[workspace] = hdr.horizon;
-  *horizon = hdr.horizon;
+  auto it = g_ws_info.find(workspace);
+  if (it == g_ws_info.end()) {
+    rg_set_error("workspace was not prepared by rg_mpc_setup (in this process)");
+    return RG_ERR_WORKSPACE;
+  }
+  *info = it->second;
   return RG_OK;
 }
 
@@ -183,6 +180,7 @@ extern "C" int rg_mpc_default_params(rg_mpc_params* p, double mass, const double
   p->max_polish_rounds = 3;
   p->cold_start_rounds = 12;
   p->cold_start_max_violations = 0;   // 0 = no limit
+  p->two_kernel_solve = 1;
   return RG_OK;
 }
 
@@ -193,7 +191,8 @@ extern "C" int rg_workspace_bytes(int n_env, int horizon, int num_legs, size_t* 
     rg_set_error("unsupported horizon %d (kernels are built for 5, 10, 20)", horizon);
     return RG_ERR_UNSUPPORTED;
   }
-  *bytes = (sizeof(RgMpcDev) + 255) & ~size_t(255);
+  // parameter block + horizon tables, then the fallback queue of the two-kernel solve for n_env envs
+  *bytes = RG_MPC_SCRATCH_OFFSET + ((offsetof(RgMpcScratch, queue) + sizeof(int32_t) * (size_t)(n_env > 0 ? n_env : 1) + 255) & ~size_t(255));
   return RG_OK;
 }
 
@@ -271,20 +270,53 @@ extern "C" int rg_mpc_setup(const rg_mpc_params* p, void* workspace, size_t work
         }
     }
   }
+  if (((uintptr_t)workspace & 255u) != 0) { rg_set_error("workspace must be 256-byte aligned"); return RG_ERR_BAD_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   rc = rg_check_cuda(cudaMemcpyAsync(workspace, &h, sizeof(h), cudaMemcpyHostToDevice, st), "rg_mpc_setup upload");
   if (rc != RG_OK) return rc;
+  // fallback queue: whatever follows the parameter block holds the list (capacity = envs it was sized for)
+  RgMpcScratch sc;
+  memset(&sc, 0, sizeof(sc));
+  const size_t avail = workspace_bytes - RG_MPC_SCRATCH_OFFSET;
+  const size_t cap = avail > offsetof(RgMpcScratch, queue) ? (avail - offsetof(RgMpcScratch, queue)) / sizeof(int32_t) : 0;
+  sc.capacity = (int32_t)(cap > 0x7fffffff ? 0x7fffffff : cap);
+  rc = rg_check_cuda(cudaMemcpyAsync((char*)workspace + RG_MPC_SCRATCH_OFFSET, &sc, offsetof(RgMpcScratch, queue), cudaMemcpyHostToDevice, st),
+                     "rg_mpc_setup scratch upload");
+  if (rc != RG_OK) return rc;
   rc = rg_check_cuda(cudaStreamSynchronize(st), "rg_mpc_setup sync");
   if (rc != RG_OK) return rc;
+  RgMpcHostInfo info;
+  info.horizon = p->horizon;
+  info.queue_capacity = sc.capacity;
+  info.two_kernel = (p->two_kernel_solve != 0 && h.cold_start_rounds > 0) ? 1 : 0;
   std::lock_guard<std::mutex> lock(g_ws_mutex);
-  g_ws_horizon[workspace] = p->horizon;
+  g_ws_info[workspace] = info;
   return RG_OK;
 }
 
 extern "C" int rg_mpc_release(const void* workspace) {
   std::lock_guard<std::mutex> lock(g_ws_mutex);
-  g_ws_horizon.erase(workspace);
+  g_ws_info.erase(workspace);
   return RG_OK;
+}
+
+extern "C" int rg_mpc_build_solve_io(const void* workspace, int n_env, const rg_mpc_io* io, void* stream) {
+  if (n_env == 0) return RG_OK;   // empty batch: nothing to validate, nothing to launch
+  if (!workspace || !io || !io->com_velocity_body || !io->base_rpy || !io->base_rpy_rate || !io->foot_contact_state ||
+      !io->foot_positions_base || !io->command || !io->contact_forces) {
+    rg_set_error("rg_mpc_build_solve: NULL argument");
+    return RG_ERR_BAD_ARG;
+  }
+  if (n_env < 0) { rg_set_error("rg_mpc_build_solve: n_env < 0"); return RG_ERR_BAD_ARG; }
+  if (((uintptr_t)io->foot_contact_state & 3u) != 0) {   // the kernel reads the four contact flags of an env as one 32-bit word
+    rg_set_error("rg_mpc_build_solve: foot_contact_state must be 4-byte aligned");
+    return RG_ERR_BAD_ARG;
+  }
+  RgMpcHostInfo info;
+  int rc = rg_mpc_workspace_info(workspace, &info);
+  if (rc != RG_OK) return rc;
+  return rg_launch_mpc((const RgMpcDev*)workspace, info.horizon, n_env, *io, info.two_kernel && info.queue_capacity >= n_env,
+                       (cudaStream_t)stream);
 }
 
 extern "C" int rg_mpc_build_solve(const void* workspace, int n_env, const float* com_velocity_body,
@@ -302,19 +334,20 @@ extern "C" int rg_mpc_build_solve_warm(const void* workspace, int n_env, const f
                                        const uint8_t* foot_contact_state, const float* foot_positions_base,
                                        const float* command, const float* com_height, float* contact_forces,
                                        float* horizon_forces, int32_t* solve_info, uint16_t* active_set_io, void* stream) {
-  if (n_env == 0) return RG_OK;   // empty batch: nothing to validate, nothing to launch
-  if (!workspace || !com_velocity_body || !base_rpy || !base_rpy_rate || !foot_contact_state ||
-      !foot_positions_base || !command || !contact_forces) {
-    rg_set_error("rg_mpc_build_solve: NULL argument");
-    return RG_ERR_BAD_ARG;
-  }
-  if (n_env < 0) { rg_set_error("rg_mpc_build_solve: n_env < 0"); return RG_ERR_BAD_ARG; }
-  int horizon = 0;
-  int rc = rg_mpc_workspace_horizon(workspace, &horizon);
-  if (rc != RG_OK) return rc;
-  return rg_launch_mpc((const RgMpcDev*)workspace, horizon, n_env, com_velocity_body, base_rpy, base_rpy_rate,
-                       foot_contact_state, foot_positions_base, command, com_height, 0, contact_forces, horizon_forces,
-                       solve_info, active_set_io, (cudaStream_t)stream);
+  rg_mpc_io io;
+  memset(&io, 0, sizeof(io));
+  io.com_velocity_body = com_velocity_body;
+  io.base_rpy = base_rpy;
+  io.base_rpy_rate = base_rpy_rate;
+  io.foot_contact_state = foot_contact_state;
+  io.foot_positions_base = foot_positions_base;
+  io.command = command;
+  io.com_height = com_height;
+  io.contact_forces = contact_forces;
+  io.horizon_forces = horizon_forces;
+  io.solve_info = solve_info;
+  io.active_set_io = active_set_io;
+  return rg_mpc_build_solve_io(workspace, n_env, &io, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

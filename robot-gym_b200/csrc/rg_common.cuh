@@ -38,6 +38,19 @@ struct RgMpcDev {
   double kinv_lin[3][RG_MAX_HORIZON * (RG_MAX_HORIZON + 1) / 2];        // K^-1 of the x/y/z channels, packed
 };
 
+// Per-workspace scratch behind the parameter block (rg_workspace_bytes(n_env, ...) sizes it for n_env envs):
+// the fallback queue of the two-kernel solve.  The lean kernel appends the envs its active-set rounds could
+// not verify; the full kernel then runs on that list and its last CTA re-arms the counters, so no memset
+// sits between launches.  One solve at a time per workspace (concurrent streams need their own workspace).
+struct RgMpcScratch {
+  int32_t queue_tail;      // number of queued envs (atomicAdd by the lean kernel)
+  int32_t done_ctas;       // ticket counter of the fallback kernel's CTAs
+  int32_t capacity;        // entries of queue[] (written by rg_mpc_setup, read-only afterwards)
+  int32_t reserved[61];
+  int32_t queue[1];        // [capacity]
+};
+#define RG_MPC_SCRATCH_OFFSET ((sizeof(RgMpcDev) + 255) & ~size_t(255))
+
 // Device image of rg_robot_params with the IK constants derived on the host.
 struct RgLegDev {
   double p[3][3];
@@ -81,9 +94,7 @@ void rg_count_launch();
 
 // launchers implemented in the .cu files
 struct rg_controller_state;
-int rg_launch_mpc(const RgMpcDev* ws, int horizon, int n_env, const float* com_vel, const float* rpy,
-                  const float* rpy_rate, const uint8_t* contacts, const float* feet, const float* command,
-                  const float* com_height, int zero_yaw, float* forces, float* horizon_forces, int32_t* info, uint16_t* active_set,
-                  cudaStream_t stream);
-// horizon stored in a prepared MPC workspace (host-side registry, falls back to a header read)
-int rg_mpc_workspace_horizon(const void* workspace, int* horizon);
+int rg_launch_mpc(const RgMpcDev* ws, int horizon, int n_env, const rg_mpc_io& io, int two_kernel, cudaStream_t stream);
+// host-side record of a workspace prepared by rg_mpc_setup (no device access on the launch path)
+struct RgMpcHostInfo { int horizon; int queue_capacity; int two_kernel; };
+int rg_mpc_workspace_info(const void* workspace, RgMpcHostInfo* info);

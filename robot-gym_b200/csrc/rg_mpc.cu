@@ -30,6 +30,8 @@
 //   warp 0                    : runs the two triangular sweeps with __shfl broadcasts.
 #include "rg_common.cuh"
 #include <math.h>
+#include <map>
+#include <mutex>
 
 #ifdef RG_DEBUG_TRACE
 // debug builds only (RG_DEBUG_TRACE=1 python -m robot_gym.cuda.build): per-iteration trace of one env
@@ -232,7 +234,8 @@ __device__ RG_HEAVY_INLINE void cholesky_rows(Smem<H>& sm, int j_begin) {
 #pragma unroll 1
   for (int j0 = j_begin; j0 < N6; j0 += 4) {
     RG_TOCL(32, N6 - 1);
-    const int w = N6 - j0 < 4 ? N6 - j0 : 4;          // panel width (the last panel of N6 = 30 has 2 columns)
+    // panel width: always 4 when 6h is a multiple of 4 (h = 10, 20); the last panel of N6 = 30 has 2 columns
+    const int w = (N6 % 4 == 0) ? 4 : (N6 - j0 < 4 ? N6 - j0 : 4);
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     const bool in_play = row_ok && i >= j0;
     if (in_play) {
@@ -812,22 +815,30 @@ __device__ __forceinline__ void chol5_block_solve(const Chol5& c, const double* 
   for (int i = 0; i < 5; ++i) c5[i] = z[i] * inv_d[i];
 }
 
-template <int H>
-__global__ void __launch_bounds__(Cfg<H>::NT, Cfg<H>::MIN_BLOCKS)
-mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
-                 const float* __restrict__ g_com_vel, const float* __restrict__ g_rpy,
-                 const float* __restrict__ g_rpy_rate, const uint8_t* __restrict__ g_contacts,
-                 const float* __restrict__ g_feet, const float* __restrict__ g_cmd,
-                 const float* __restrict__ g_com_height, int zero_yaw,
-                 float* __restrict__ g_forces, float* __restrict__ g_hforces, int32_t* __restrict__ g_info,
-                 uint16_t* __restrict__ g_active) {
+// One env's stance QP, executed by the whole CTA.
+// LEAN = true : the verified active-set rounds only -- no interior-point state or code (the registers that frees
+//               are most of the kernel's local-memory frame).  An env whose rounds do not verify within the
+//               cold-start budget is appended to the fallback queue and gets no output from this call.
+// LEAN = false: the complete solver (cold start unless skip_cold, interior point, escalation ladder).
+template <int H, bool LEAN>
+__device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restrict__ ws, RgMpcScratch* __restrict__ scratch,
+                                          const int env, const bool skip_cold,
+                                          const rg_mpc_io& io) {
   using C = Cfg<H>;
+  const float* __restrict__ g_com_vel = io.com_velocity_body;
+  const float* __restrict__ g_rpy = io.base_rpy;
+  const float* __restrict__ g_rpy_rate = io.base_rpy_rate;
+  const uint8_t* __restrict__ g_contacts = io.foot_contact_state;
+  const float* __restrict__ g_feet = io.foot_positions_base;
+  const float* __restrict__ g_cmd = io.command;
+  const float* __restrict__ g_com_height = io.com_height;
+  const int zero_yaw = io.zero_yaw;
+  float* __restrict__ g_forces = io.contact_forces;
+  float* __restrict__ g_hforces = io.horizon_forces;
+  double* __restrict__ g_hforces64 = io.horizon_forces_f64;
+  int32_t* __restrict__ g_info = io.solve_info;
+  uint16_t* __restrict__ g_active = io.active_set_io;
   constexpr int N6 = C::N6;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<H>& sm = *reinterpret_cast<Smem<H>*>(smem_raw);
-
-  const int env = blockIdx.x;
-  if (env >= n_env) return;
   const int tid = threadIdx.x;
 #ifdef RG_DEBUG_TRACE
   const long long rg_tstart_ = clock64();
@@ -841,6 +852,16 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
 #endif
   const int t_blk = tid >> 2, leg = tid & 3;
   const bool is_blk = tid < C::NB;
+
+  // the host record of this workspace may be stale (memory reused without rg_mpc_release): never index the
+  // tables with the wrong horizon
+  if (ws->magic != RG_WS_MAGIC_MPC || ws->horizon != H) {
+    for (int i = tid; i < 12; i += blockDim.x) g_forces[12 * (size_t)env + i] = 0.f;
+    if (g_hforces) for (int i = tid; i < 12 * H; i += blockDim.x) g_hforces[12 * H * (size_t)env + i] = 0.f;
+    if (g_hforces64) for (int i = tid; i < 12 * H; i += blockDim.x) g_hforces64[12 * H * (size_t)env + i] = 0.0;
+    if (g_info && tid < 4) g_info[4 * (size_t)env + tid] = tid == RG_INFO_STATUS ? RG_STATUS_BAD_WORKSPACE : 0;
+    return;
+  }
 
   // ---------------------------------------------------------------- parameters (uniform loads)
   const double dt = ws->dt, two_alpha = 2.0 * ws->alpha;
@@ -873,6 +894,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   if (n_stance == 0) {   // every force pinned to zero by the bounds
     for (int i = tid; i < 12; i += blockDim.x) g_forces[12 * (size_t)env + i] = 0.f;
     if (g_hforces) for (int i = tid; i < 12 * H; i += blockDim.x) g_hforces[12 * H * (size_t)env + i] = 0.f;
+    if (g_hforces64) for (int i = tid; i < 12 * H; i += blockDim.x) g_hforces64[12 * H * (size_t)env + i] = 0.0;
     if (g_info && tid < 4) g_info[4 * (size_t)env + tid] = tid == RG_INFO_STATUS ? (RG_STATUS_NO_STANCE | RG_STATUS_POLISHED) : 0;
     if (g_active && is_blk) g_active[(size_t)env * C::NB + tid] = RG_ACTIVE_SET_UNKNOWN;
     return;
@@ -1060,7 +1082,8 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   const double lo_b[5] = {0.0, 0.0, 0.0, 0.0, fzmin};
 
   // ---------------------------------------------------------------- interior point
-  double u[3] = {0.0, 0.0, 0.0}, s[10], lam[10];
+  // (the lean instantiation declares the interior-point state with one element and never touches it)
+  double u[3] = {0.0, 0.0, 0.0}, s[LEAN ? 1 : 10], lam[LEAN ? 1 : 10];
   // strictly feasible start: every stance foot carries its share of the weight
   const double fz0 = fmin(0.5 * (fzmin + fzmax), fmax(2.0 * fzmin, ws->gravity / (inv_mass * n_stance)));
   u[2] = active_blk ? fz0 : 0.0;
@@ -1070,7 +1093,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
     block_reduce<C::NW>(dsum, qmax, dmn, sm.red);
   }
   const double qscale = fmax(1.0, qmax);
-  {
+  if constexpr (!LEAN) {
     double c5[5];
     g_mul(u, mu, c5);
 #pragma unroll
@@ -1108,9 +1131,10 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   const int cold_rounds = ws->cold_start_rounds;
   const double cold_max_viol = (double)ws->cold_start_max_violations;
 #pragma unroll 1
-  for (int attempt = cold_rounds > 0 ? -1 : 0; attempt < 3 && !done; ++attempt) {
+  for (int attempt = (cold_rounds > 0 && !skip_cold) ? -1 : 0; attempt < (LEAN ? 0 : 3) && !done; ++attempt) {
     bool converged = false, ipm_dead = false, handed_over = false;
-    const bool cold = attempt < 0;
+    const bool cold = LEAN || attempt < 0;
+    if constexpr (!LEAN) {
     if (!cold) {
     if (iters == 0) {
       // Centred start s lam = mu0 with mu0 commensurate with the dual residual at the start: with mu0 far
@@ -1272,13 +1296,16 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       continue;
     }
     }   // !cold
+    }   // !LEAN
 
     RG_TOC(6);
     // -------------------------------------------------------------- active-set polish
     unsigned act = 0;
     if (!cold) {
+      if constexpr (!LEAN) {
 #pragma unroll
-      for (int r = 0; r < 10; ++r) if (active_blk && lam[r] > 0.03 * s[r]) act |= 1u << r;
+        for (int r = 0; r < 10; ++r) if (active_blk && lam[r] > 0.03 * s[r]) act |= 1u << r;
+      }
     } else if (warm_act != RG_ACTIVE_SET_UNKNOWN) {
       // warm start: the verified active set of this block from the previous solve of the same env
       // (consecutive control steps see almost the same problem); wrong guesses are repaired by the rounds
@@ -1504,6 +1531,7 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       break;
     }
     if (ipm_dead) break;
+    if constexpr (LEAN) break;
     if (cold) {
       // The cold start gave up: move the interior point's start from the safe point towards the last
       // active-set iterate, as far as strict feasibility allows (ratio test), keeping r_p = 0.
@@ -1520,17 +1548,29 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       }
       block_reduce<C::NW>(dsum, dmx, thmax, sm.red);
       const double theta = RG_IPM_WARM * thmax;
-      if (active_blk && theta > 0.0) {
+      if constexpr (!LEAN) {
+        if (active_blk && theta > 0.0) {
 #pragma unroll
-        for (int d = 0; d < 3; ++d) u[d] += theta * dir[d];
-        double c5[5];
-        g_mul(u, mu, c5);
+          for (int d = 0; d < 3; ++d) u[d] += theta * dir[d];
+          double c5[5];
+          g_mul(u, mu, c5);
 #pragma unroll
-        for (int r = 0; r < 5; ++r) { s[r] = hv_up[r] - c5[r]; s[5 + r] = c5[r] - lo_b[r]; }
+          for (int r = 0; r < 5; ++r) { s[r] = hv_up[r] - c5[r]; s[5 + r] = c5[r] - lo_b[r]; }
+        }
       }
       continue;
     }
     tol = fmax(tol * 1e-2, 1e-9);   // float64 interior-point iterates are trustworthy down to ~1e-9 here
+  }
+  if constexpr (LEAN) {
+    if (!done) {
+      // not verified by the rounds alone: the full solver takes this env from the fallback queue
+      if (tid == 0) {
+        const int slot = atomicAdd(&scratch->queue_tail, 1);
+        scratch->queue[slot] = env;
+      }
+      return;
+    }
   }
   if (!done) {
 #pragma unroll
@@ -1559,6 +1599,10 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
       float* o = g_hforces + 12 * H * (size_t)env + 12 * t_blk + 3 * leg;
       o[0] = fx; o[1] = fy; o[2] = fz;
     }
+    if (g_hforces64) {
+      double* o = g_hforces64 + 12 * H * (size_t)env + 12 * t_blk + 3 * leg;
+      o[0] = active_blk ? -u_out[0] : 0.0; o[1] = active_blk ? -u_out[1] : 0.0; o[2] = active_blk ? -u_out[2] : 0.0;
+    }
   }
   if (g_active && is_blk) g_active[(size_t)env * C::NB + tid] = (uint16_t)((done && active_blk) ? act_out : RG_ACTIVE_SET_UNKNOWN);
   if (g_info && tid == 0) {
@@ -1570,30 +1614,96 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, int n_env,
   }
 }
 
+// Grid of the lean kernel and of the single-kernel path: one CTA per env (blockIdx.x = env).
+template <int H, bool LEAN>
+__global__ void __launch_bounds__(Cfg<H>::NT, Cfg<H>::MIN_BLOCKS)
+mpc_solve_kernel(const RgMpcDev* __restrict__ ws, RgMpcScratch* __restrict__ scratch, int n_env, const rg_mpc_io io) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<H>& sm = *reinterpret_cast<Smem<H>*>(smem_raw);
+  const int env = blockIdx.x;
+  if (env >= n_env) return;
+  solve_env<H, LEAN>(sm, ws, scratch, env, false, io);
+}
+
+// Second kernel of the two-kernel solve: the complete solver on the envs the lean kernel queued.  Persistent CTAs
+// stride over the list (it is empty for trot / walk batches: the launch then costs a few microseconds); the cold
+// start is skipped -- the lean kernel has just spent its budget on exactly those rounds.  The last CTA to finish
+// re-arms the queue counters for the next solve.
 template <int H>
-int launch_h(const RgMpcDev* ws, int n_env, const float* com_vel, const float* rpy, const float* rpy_rate,
-             const uint8_t* contacts, const float* feet, const float* command, const float* com_height,
-             int zero_yaw, float* forces, float* horizon_forces, int32_t* info, uint16_t* active_set, cudaStream_t stream) {
-  const size_t smem = sizeof(Smem<H>);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mpc_solve_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return rg_check_cuda(e, "cudaFuncSetAttribute(mpc_solve_kernel)");
-    // the default carveout leaves room for only ~5 CTAs: ask for what MIN_BLOCKS resident CTAs need and no
-    // more, so that the rest of the 228 KB stays L1 (register spills and the parameter block live there)
-#ifndef RG_CARVEOUT_PCT
-    const int need_kb = (int)((Cfg<H>::MIN_BLOCKS * (smem + 1024) + 1023) / 1024);
-    int carveout = (need_kb * 100 + 227) / 228 + 1;
-    if (carveout > 100) carveout = 100;
-#else
-    const int carveout = RG_CARVEOUT_PCT;
-#endif
-    e = cudaFuncSetAttribute(mpc_solve_kernel<H>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
-    if (e != cudaSuccess) return rg_check_cuda(e, "cudaFuncSetAttribute(carveout)");
-    attr_set = true;
+__global__ void __launch_bounds__(Cfg<H>::NT, Cfg<H>::MIN_BLOCKS)
+mpc_fallback_kernel(const RgMpcDev* __restrict__ ws, RgMpcScratch* __restrict__ scratch, int n_env, const rg_mpc_io io) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<H>& sm = *reinterpret_cast<Smem<H>*>(smem_raw);
+  const int count = min(scratch->queue_tail, min(scratch->capacity, n_env));
+  for (int q = blockIdx.x; q < count; q += gridDim.x) {
+    const int env = scratch->queue[q];
+    if (env >= 0 && env < n_env)
+      solve_env<H, false>(sm, ws, scratch, env, true, io);
+    __syncthreads();   // shared memory is reused by the next env of this CTA
   }
-  mpc_solve_kernel<H><<<n_env, Cfg<H>::NT, smem, stream>>>(ws, n_env, com_vel, rpy, rpy_rate, contacts, feet, command,
-                                                            com_height, zero_yaw, forces, horizon_forces, info, active_set);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&scratch->done_ctas, 1) == (int)gridDim.x - 1) {   // every CTA has read queue_tail and finished
+      scratch->queue_tail = 0;
+      scratch->done_ctas = 0;
+    }
+  }
+}
+
+// Dynamic shared memory above 48 KB (h = 20) and the carveout are per-device function attributes: set them once
+// per (kernel, device), under a lock -- a process may drive several GPUs from several threads.
+int configure_kernel(const void* kernel, size_t smem, int min_blocks, const char* what) {
+  static std::mutex mutex;
+  static std::map<const void*, unsigned long long> configured;   // kernel -> bit d set: done for device d
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return rg_check_cuda(e, "cudaGetDevice");
+  std::lock_guard<std::mutex> lock(mutex);
+  unsigned long long& mask = configured[kernel];
+  if (dev < 64 && ((mask >> dev) & 1ull)) return RG_OK;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return rg_check_cuda(e, what);
+  // the default carveout leaves room for only ~5 CTAs: ask for what MIN_BLOCKS resident CTAs need and no
+  // more, so that the rest of the 228 KB stays L1 (local-memory traffic and the parameter block live there)
+#ifndef RG_CARVEOUT_PCT
+  const int need_kb = (int)((min_blocks * (smem + 1024) + 1023) / 1024);
+  int carveout = (need_kb * 100 + 227) / 228 + 1;
+  if (carveout > 100) carveout = 100;
+#else
+  const int carveout = RG_CARVEOUT_PCT;
+#endif
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+  if (e != cudaSuccess) return rg_check_cuda(e, what);
+  if (dev < 64) mask |= 1ull << dev;
+  return RG_OK;
+}
+
+template <int H>
+int launch_h(const RgMpcDev* ws, int n_env, const rg_mpc_io& io, int two_kernel, cudaStream_t stream) {
+  const size_t smem = sizeof(Smem<H>);
+  RgMpcScratch* scratch = (RgMpcScratch*)((char*)ws + RG_MPC_SCRATCH_OFFSET);
+  int rc;
+  if (two_kernel) {
+    // lean active-set kernel on every env, then the complete solver on whatever it queued
+    rc = configure_kernel((const void*)mpc_solve_kernel<H, true>, smem, Cfg<H>::MIN_BLOCKS, "cudaFuncSetAttribute(mpc_solve_kernel lean)");
+    if (rc != RG_OK) return rc;
+    rc = configure_kernel((const void*)mpc_fallback_kernel<H>, smem, Cfg<H>::MIN_BLOCKS, "cudaFuncSetAttribute(mpc_fallback_kernel)");
+    if (rc != RG_OK) return rc;
+    mpc_solve_kernel<H, true><<<n_env, Cfg<H>::NT, smem, stream>>>(ws, scratch, n_env, io);
+    rg_count_launch();
+    rc = rg_check_cuda(cudaGetLastError(), "mpc_solve_kernel (lean) launch");
+    if (rc != RG_OK) return rc;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = n_env < sms * 2 ? n_env : sms * 2;
+    mpc_fallback_kernel<H><<<grid, Cfg<H>::NT, smem, stream>>>(ws, scratch, n_env, io);
+    rg_count_launch();
+    return rg_check_cuda(cudaGetLastError(), "mpc_fallback_kernel launch");
+  }
+  rc = configure_kernel((const void*)mpc_solve_kernel<H, false>, smem, Cfg<H>::MIN_BLOCKS, "cudaFuncSetAttribute(mpc_solve_kernel)");
+  if (rc != RG_OK) return rc;
+  mpc_solve_kernel<H, false><<<n_env, Cfg<H>::NT, smem, stream>>>(ws, scratch, n_env, io);
   rg_count_launch();
   return rg_check_cuda(cudaGetLastError(), "mpc_solve_kernel launch");
 }
@@ -1646,14 +1756,11 @@ extern "C" int rg_debug_chol_solve(int horizon, const double* a_dense, const dou
   }
 }
 
-int rg_launch_mpc(const RgMpcDev* ws, int horizon, int n_env, const float* com_vel, const float* rpy,
-                  const float* rpy_rate, const uint8_t* contacts, const float* feet, const float* command,
-                  const float* com_height, int zero_yaw, float* forces, float* horizon_forces, int32_t* info,
-                  uint16_t* active_set, cudaStream_t stream) {
+int rg_launch_mpc(const RgMpcDev* ws, int horizon, int n_env, const rg_mpc_io& io, int two_kernel, cudaStream_t stream) {
   switch (horizon) {
-    case 5: return launch_h<5>(ws, n_env, com_vel, rpy, rpy_rate, contacts, feet, command, com_height, zero_yaw, forces, horizon_forces, info, active_set, stream);
-    case 10: return launch_h<10>(ws, n_env, com_vel, rpy, rpy_rate, contacts, feet, command, com_height, zero_yaw, forces, horizon_forces, info, active_set, stream);
-    case 20: return launch_h<20>(ws, n_env, com_vel, rpy, rpy_rate, contacts, feet, command, com_height, zero_yaw, forces, horizon_forces, info, active_set, stream);
+    case 5: return launch_h<5>(ws, n_env, io, two_kernel, stream);
+    case 10: return launch_h<10>(ws, n_env, io, two_kernel, stream);
+    case 20: return launch_h<20>(ws, n_env, io, two_kernel, stream);
     default:
       rg_set_error("unsupported horizon %d (kernels are built for 5, 10, 20)", horizon);
       return RG_ERR_UNSUPPORTED;

@@ -703,13 +703,23 @@ extern "C" int rg_control_step(const void* mpc_ws, const void* robot_ws, int n_e
   rg_count_launch();
   int rc = rg_check_cuda(cudaGetLastError(), "step_prologue_kernel launch");
   if (rc != RG_OK) return rc;
-  int horizon = 0;
-  rc = rg_mpc_workspace_horizon(mpc_ws, &horizon);
+  RgMpcHostInfo info;
+  rc = rg_mpc_workspace_info(mpc_ws, &info);
   if (rc != RG_OK) return rc;
   // TorqueStanceLegController.get_action zeroes the yaw before the solve ("yaw aligned world frame")
-  rc = rg_launch_mpc((const RgMpcDev*)mpc_ws, horizon, n_env, s->com_velocity_body, s->base_rpy, s->base_rpy_rate,
-                     s->mpc_contact_state, s->foot_positions_base, s->command, nullptr, /*zero_yaw=*/1,
-                     s->contact_forces, nullptr, s->solve_info, s->mpc_active_set, st);
+  rg_mpc_io io;
+  memset(&io, 0, sizeof(io));
+  io.com_velocity_body = s->com_velocity_body;
+  io.base_rpy = s->base_rpy;
+  io.base_rpy_rate = s->base_rpy_rate;
+  io.foot_contact_state = s->mpc_contact_state;
+  io.foot_positions_base = s->foot_positions_base;
+  io.command = s->command;
+  io.contact_forces = s->contact_forces;
+  io.solve_info = s->solve_info;
+  io.active_set_io = s->mpc_active_set;
+  io.zero_yaw = 1;
+  rc = rg_launch_mpc((const RgMpcDev*)mpc_ws, info.horizon, n_env, io, info.two_kernel && info.queue_capacity >= n_env, st);
   if (rc != RG_OK) return rc;
   step_epilogue_kernel<<<grid_for(4 * n_env, 256), 256, 0, st>>>((const RgRobotDev*)robot_ws, n_env, *s);
   rg_count_launch();

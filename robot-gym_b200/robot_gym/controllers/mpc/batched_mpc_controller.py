@@ -92,7 +92,7 @@ class BatchedMPCController(Controller):
                 setattr(self.mpc_params, key, value)
         self.robot_params = robot_params_from_description(robot, c)
         with torch.cuda.device(dev):
-            self._mpc_ws = rg.MpcWorkspace(self.mpc_params, device=dev)
+            self._mpc_ws = rg.MpcWorkspace(self.mpc_params, device=dev, max_envs=n)
             self._robot_ws = rg.RobotWorkspace(self.robot_params, device=dev)
         self._kinematics = BatchedKinematics(self._robot_ws, dev)
         self._window = int(self.robot_params.velocity_window)
@@ -124,6 +124,8 @@ class BatchedMPCController(Controller):
         self.reset_time = z((n,), f64)
         self.time_since_reset = z((n,), f64)
         self._mpc_controller = _LocomotionHandle(self)
+        self._state = self._build_state()
+        self._input_cache = {}
         self.update_controller_params(self.get_standing_action())
         self.reset()
 
@@ -204,21 +206,26 @@ class BatchedMPCController(Controller):
         return self.action
 
     # ------------------------------------------------------------------ batched step
-    def step(self):
-        r = self._robot
-        n = self.num_envs
-        torch.sub(self._clock(), self.reset_time, out=self.time_since_reset)
-        st = rg.ControllerState()
+    # (field of rg_controller_state, robot getter, dtype, trailing shape, pointer alignment)
+    _ROBOT_INPUTS = (
+        ("foot_contacts", "GetFootContacts", torch.uint8, (4,), 4),
+        ("base_velocity_world", "GetBaseVelocity", torch.float32, (3,), 4),
+        ("base_orientation_xyzw", "GetTrueBaseOrientation", torch.float32, (4,), 4),
+        ("base_rpy", "GetBaseRollPitchYaw", torch.float32, (3,), 4),
+        ("base_rpy_rate", "GetBaseRollPitchYawRate", torch.float32, (3,), 4),
+        ("foot_positions_base", "GetFootPositionsInBaseFrame", torch.float32, (12,), 4),
+        ("motor_angles", "GetMotorAngles", torch.float32, (12,), 4),
+    )
+
+    def _build_state(self):
+        """The ``rg_controller_state`` of this controller, built ONCE: every pointer to a controller-owned
+        tensor is fixed for the controller's lifetime; ``step`` only refreshes the robot-provided inputs whose
+        storage changed since the previous step."""
+        n, dev = self.num_envs, self.device
         f32, f64, i32, u8 = torch.float32, torch.float64, torch.int32, torch.uint8
-        P = rg._ptr
+        P = lambda t, dtype, tail=None, **kw: rg._ptr(t, dtype, tail, n=n, device=dev, **kw)
+        st = rg.ControllerState()
         st.time_since_reset = P(self.time_since_reset, f64)
-        st.foot_contacts = P(r.GetFootContacts(), u8, (4,))
-        st.base_velocity_world = P(r.GetBaseVelocity(), f32, (3,))
-        st.base_orientation_xyzw = P(r.GetTrueBaseOrientation(), f32, (4,))
-        st.base_rpy = P(r.GetBaseRollPitchYaw(), f32, (3,))
-        st.base_rpy_rate = P(r.GetBaseRollPitchYawRate(), f32, (3,))
-        st.foot_positions_base = P(r.GetFootPositionsInBaseFrame().view(n, 12), f32, (12,))
-        st.motor_angles = P(r.GetMotorAngles(), f32, (12,))
         st.command = P(self.command, f32, (3,))
         st.vel_window = P(self.vel_window, f64)
         st.vel_window_sum = P(self.vel_window_sum, f64)
@@ -233,17 +240,45 @@ class BatchedMPCController(Controller):
         st.desired_leg_state = P(self.desired_leg_state, i32)
         st.leg_state = P(self.leg_state, i32)
         st.normalized_phase = P(self.normalized_phase, f64)
-        st.mpc_contact_state = P(self.mpc_contact_state, u8)
+        st.mpc_contact_state = P(self.mpc_contact_state, u8, align=4)
         st.swing_foot_target = P(self.swing_foot_target, f32)
         st.com_velocity_body = P(self.com_velocity_body, f32)
         st.contact_forces = P(self.contact_forces, f32)
         st.motor_torques = P(self.motor_torques, f32)
         st.solve_info = P(self.solve_info, i32)
         st.action = P(self.action, f32)
+        return st
+
+    def _refresh_inputs(self):
+        """Pull the robot getters (robot.py:79-236,389-397).  A tensor whose storage, shape and dtype are the ones
+        validated last step is not validated again; anything new is checked for dtype, contiguity, [N, ...]
+        shape, device and alignment before its pointer reaches a kernel."""
+        n, cache, st = self.num_envs, self._input_cache, self._state
+        for field, getter, dtype, tail, align in self._ROBOT_INPUTS:
+            t = getattr(self._robot, getter)()
+            if field == "foot_positions_base" and isinstance(t, torch.Tensor) and t.dim() == 3:
+                t = t.view(n, 12) if t.is_contiguous() else t.reshape(n, 12)
+            key = (t.data_ptr(), t.shape, t.dtype) if isinstance(t, torch.Tensor) else None
+            if key is None or cache.get(field) != key:
+                setattr(st, field, rg._ptr(t, dtype, tail, n=n, device=self.device, align=align))
+                cache[field] = (t.data_ptr(), t.shape, t.dtype)
+            cache[field + "_ref"] = t          # keep the storage alive until the kernels have consumed it
+
+    def step(self):
+        torch.sub(self._clock(), self.reset_time, out=self.time_since_reset)
+        self._refresh_inputs()
         with torch.cuda.device(self.device):
-            rg.check(rg.load().rg_control_step(self._mpc_ws.ptr, self._robot_ws.ptr, n, ctypes.byref(st),
-                                               rg.current_stream_ptr()))
+            rg.check(rg.load().rg_control_step(self._mpc_ws.ptr, self._robot_ws.ptr, self.num_envs,
+                                               ctypes.byref(self._state), rg.current_stream_ptr()))
         return self.action
+
+    def unverified_count(self):
+        """Number of envs (device scalar, no synchronisation) whose last stance QP did NOT end in a verified KKT
+        point (neither RG_STATUS_POLISHED nor RG_STATUS_NO_STANCE).  The reference's OSQP path returns forces only
+        on OSQP_SOLVED; here such an env still gets forces -- the best interior-point iterate, feasible by
+        construction -- and this counter is the signal: 0 in every batch measured so far."""
+        status = self.solve_info[:, rg.RG_INFO_STATUS]
+        return ((status & (rg.RG_STATUS_POLISHED | rg.RG_STATUS_NO_STANCE)) == 0).sum()
 
     # ------------------------------------------------------------------ rollout statistics
     def rollout_stats(self):

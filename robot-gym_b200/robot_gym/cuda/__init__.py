@@ -22,11 +22,12 @@ RG_LEG_SWING, RG_LEG_STANCE, RG_LEG_EARLY_CONTACT, RG_LEG_LOSE_CONTACT = 0, 1, 2
 RG_INFO_IPM_ITERS, RG_INFO_POLISH_ROUNDS, RG_INFO_STATUS, RG_INFO_NUM_ACTIVE = 0, 1, 2, 3
 RG_STATUS_POLISHED, RG_STATUS_IPM_CONVERGED, RG_STATUS_NO_STANCE, RG_STATUS_NUMERIC = 1, 2, 4, 8
 RG_STATUS_ACTIVE_SET_ONLY = 16
+RG_STATUS_BAD_WORKSPACE = 32
 
 # every symbol include/rg_cuda.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
     "rg_mpc_default_params", "rg_workspace_bytes", "rg_mpc_setup", "rg_mpc_release", "rg_mpc_build_solve",
-    "rg_mpc_build_solve_warm",
+    "rg_mpc_build_solve_warm", "rg_mpc_build_solve_io",
     "rg_robot_calibrate_ik", "rg_robot_workspace_bytes", "rg_robot_setup",
     "rg_gait_step", "rg_com_velocity_update", "rg_swing_targets", "rg_leg_ik", "rg_leg_fk", "rg_state_from_sim",
     "rg_force_to_torque", "rg_pack_hybrid_action", "rg_control_step", "rg_hybrid_motor_torque",
@@ -43,7 +44,16 @@ class MpcParams(Structure):
         ("fz_min", c_double), ("desired_body_height", c_double), ("ipm_tol", c_double),
         ("max_ipm_iters", c_int32), ("max_polish_rounds", c_int32),
         ("cold_start_rounds", c_int32), ("cold_start_max_violations", c_int32),
+        ("two_kernel_solve", c_int32), ("reserved_", c_int32),
     ]
+
+
+class MpcIo(Structure):
+    """``rg_mpc_io`` (device pointers + flags)."""
+    _fields_ = [(name, c_void_p) for name in (
+        "com_velocity_body", "base_rpy", "base_rpy_rate", "foot_contact_state", "foot_positions_base", "command",
+        "com_height", "contact_forces", "horizon_forces", "solve_info", "active_set_io", "horizon_forces_f64")] + [
+        ("zero_yaw", c_int32), ("reserved_", c_int32)]
 
 
 class LegChain(Structure):
@@ -116,6 +126,7 @@ def load(build_if_missing: bool = False):
     lib.rg_mpc_release.argtypes = [c_void_p]
     lib.rg_mpc_build_solve.argtypes = [c_void_p, c_int] + [c_void_p] * 10 + [c_void_p]
     lib.rg_mpc_build_solve_warm.argtypes = [c_void_p, c_int] + [c_void_p] * 11 + [c_void_p]
+    lib.rg_mpc_build_solve_io.argtypes = [c_void_p, c_int, POINTER(MpcIo), c_void_p]
     lib.rg_robot_calibrate_ik.argtypes = [POINTER(RobotParams), POINTER(c_double)]
     lib.rg_robot_workspace_bytes.argtypes = [POINTER(c_size_t)]
     lib.rg_robot_setup.argtypes = [POINTER(RobotParams), c_void_p, c_size_t, c_void_p]
@@ -155,8 +166,10 @@ def launch_count() -> int:
 
 
 # ------------------------------------------------------------------------------------------ tensors
-def _ptr(t, dtype, shape_tail=None, allow_none=False):
-    """Device pointer of a contiguous CUDA tensor after dtype/shape checks."""
+def _ptr(t, dtype, shape_tail=None, allow_none=False, n=None, device=None, align=1):
+    """Device pointer of a contiguous CUDA tensor after dtype / shape / device / alignment checks.
+    ``n``: required leading dimension (the kernels index n_env rows: a shorter tensor would be read out of
+    bounds); ``device``: the device the call runs on; ``align``: required pointer alignment in bytes."""
     import torch
     if t is None:
         if allow_none:
@@ -170,6 +183,12 @@ def _ptr(t, dtype, shape_tail=None, allow_none=False):
         raise ValueError("tensor must be contiguous")
     if shape_tail is not None and tuple(t.shape[1:]) != tuple(shape_tail):
         raise ValueError(f"expected shape [N,{','.join(map(str, shape_tail))}], got {tuple(t.shape)}")
+    if n is not None and (t.dim() == 0 or t.shape[0] != n):
+        raise ValueError(f"expected {n} rows (one per env), got shape {tuple(t.shape)}")
+    if device is not None and t.device != torch.device(device):
+        raise ValueError(f"tensor lives on {t.device}, the call runs on {torch.device(device)}")
+    if align > 1 and t.data_ptr() % align:
+        raise ValueError(f"tensor storage must be {align}-byte aligned")
     return c_void_p(t.data_ptr())
 
 
@@ -186,15 +205,19 @@ def default_mpc_params(mass, inertia9, desired_body_height, horizon=10) -> MpcPa
 
 
 class MpcWorkspace:
-    """Device-resident parameter block + horizon tables prepared by ``rg_mpc_setup``."""
+    """Device-resident parameter block + horizon tables prepared by ``rg_mpc_setup``, followed by the fallback
+    queue of the two-kernel solve for batches of up to ``max_envs`` envs (4 bytes each).  Larger batches are
+    still solved, by the single complete kernel.  One solve at a time per workspace: concurrent solves on
+    different streams need a workspace each."""
 
-    def __init__(self, params: MpcParams, device="cuda"):
+    def __init__(self, params: MpcParams, device="cuda", max_envs=65536):
         import torch
         lib = load()
         nbytes = c_size_t()
-        check(lib.rg_workspace_bytes(0, params.horizon, params.num_legs, ctypes.byref(nbytes)))
+        check(lib.rg_workspace_bytes(int(max_envs), params.horizon, params.num_legs, ctypes.byref(nbytes)))
         self.params = params
         self.horizon = int(params.horizon)
+        self.max_envs = int(max_envs)
         self.buffer = torch.zeros(nbytes.value, dtype=torch.uint8, device=device)
         with torch.cuda.device(self.buffer.device):
             check(lib.rg_mpc_setup(ctypes.byref(params), c_void_p(self.buffer.data_ptr()), nbytes.value,
@@ -237,29 +260,44 @@ def calibrate_ik(params: RobotParams, reference_motor_angles) -> None:
 
 def mpc_build_solve(ws: MpcWorkspace, com_velocity_body, base_rpy, base_rpy_rate, foot_contact_state,
                     foot_positions_base, command, com_height=None, contact_forces=None,
-                    horizon_forces=None, solve_info=None, want_horizon=False, want_info=True, active_set=None):
+                    horizon_forces=None, solve_info=None, want_horizon=False, want_info=True, active_set=None,
+                    zero_yaw=False, horizon_forces_f64=None):
     """``rg_mpc_build_solve`` (``rg_mpc_build_solve_warm`` when ``active_set`` -- an ``[N, 4*horizon]`` int16 tensor
-    initialised to -1, see ``new_active_set`` -- is given) on the current stream.
-    Returns (contact_forces, horizon_forces, solve_info)."""
+    initialised to -1, see ``new_active_set`` -- is given) on the current stream.  ``base_rpy`` is used as given:
+    pass a yaw-aligned attitude (yaw = 0) to reproduce TorqueStanceLegController (the controller's fused step
+    zeroes it itself) or set ``zero_yaw``.  ``horizon_forces_f64``: optional ``[N,h,12]`` float64 output (the
+    unrounded solution; goes through ``rg_mpc_build_solve_io``).  Returns (contact_forces, horizon_forces, solve_info)."""
     import torch
     n = base_rpy.shape[0]
     dev = base_rpy.device
+    if ws.buffer.device != dev:
+        raise ValueError(f"workspace lives on {ws.buffer.device}, inputs on {dev}")
     if contact_forces is None:
         contact_forces = torch.empty((n, 12), dtype=torch.float32, device=dev)
     if horizon_forces is None and want_horizon:
         horizon_forces = torch.empty((n, ws.horizon, 12), dtype=torch.float32, device=dev)
     if solve_info is None and want_info:
         solve_info = torch.empty((n, 4), dtype=torch.int32, device=dev)
-    hf = None if horizon_forces is None else _ptr(horizon_forces.view(n, ws.horizon * 12), torch.float32, (ws.horizon * 12,))
-    check(load().rg_mpc_build_solve_warm(
-        ws.ptr, n,
-        _ptr(com_velocity_body, torch.float32, (3,)), _ptr(base_rpy, torch.float32, (3,)),
-        _ptr(base_rpy_rate, torch.float32, (3,)), _ptr(foot_contact_state, torch.uint8, (4,)),
-        _ptr(foot_positions_base.view(n, 12), torch.float32, (12,)), _ptr(command, torch.float32, (3,)),
-        _ptr(com_height, torch.float32, (), allow_none=True),
-        _ptr(contact_forces, torch.float32, (12,)), hf,
-        _ptr(solve_info, torch.int32, (4,), allow_none=True),
-        _ptr(active_set, torch.int16, (4 * ws.horizon,), allow_none=True), current_stream_ptr()))
+    P = lambda t, dtype, tail, **kw: _ptr(t, dtype, tail, n=n, device=dev, **kw)
+    hf = None if horizon_forces is None else P(horizon_forces.view(n, ws.horizon * 12), torch.float32, (ws.horizon * 12,))
+    args = (ws.ptr, n,
+            P(com_velocity_body, torch.float32, (3,)), P(base_rpy, torch.float32, (3,)),
+            P(base_rpy_rate, torch.float32, (3,)), P(foot_contact_state, torch.uint8, (4,), align=4),
+            P(foot_positions_base.view(n, 12), torch.float32, (12,)), P(command, torch.float32, (3,)),
+            P(com_height, torch.float32, (), allow_none=True),
+            P(contact_forces, torch.float32, (12,)), hf,
+            P(solve_info, torch.int32, (4,), allow_none=True))
+    with torch.cuda.device(dev):
+        if zero_yaw or horizon_forces_f64 is not None:
+            io = MpcIo(*[a if a is None or isinstance(a, int) else a.value for a in args[2:]],
+                       None if active_set is None else P(active_set, torch.int16, (4 * ws.horizon,)).value,
+                       None if horizon_forces_f64 is None else P(horizon_forces_f64.view(n, ws.horizon * 12), torch.float64, (ws.horizon * 12,)).value,
+                       1 if zero_yaw else 0, 0)
+            check(load().rg_mpc_build_solve_io(ws.ptr, n, ctypes.byref(io), current_stream_ptr()))
+        elif active_set is None:
+            check(load().rg_mpc_build_solve(*args, current_stream_ptr()))
+        else:
+            check(load().rg_mpc_build_solve_warm(*args, P(active_set, torch.int16, (4 * ws.horizon,)), current_stream_ptr()))
     return contact_forces, horizon_forces, solve_info
 
 

@@ -141,3 +141,20 @@ def make_state_sequence(n_env, n_steps, description, schedule_ctrl=None, seed=SE
         st.foot_contacts = np.logical_xor(planned, flip).astype(np.uint8)
         seq.append(st)
     return seq
+
+
+CHUNK = 4096
+
+
+def make_states_sharded(lo, hi, description, schedule_ctrl=None, seed=SEED, **kwargs):
+    """Envs [lo, hi) of an unbounded, PREFIX-STABLE global batch: the batch is the concatenation of 4096-env chunks,
+    chunk c drawn by ``make_states(4096, ..., seed=seed + c)``.  A rank's shard therefore does not depend on how
+    many ranks (or envs) the job has -- rank 0 of a 1-, 2-, 4- or 8-GPU run solves exactly the same first chunk,
+    which is ``make_states(4096, description)`` itself, the single-GPU benchmark batch."""
+    lo, hi = int(lo), int(hi)
+    parts = []
+    for c in range(lo // CHUNK, (max(hi, lo + 1) - 1) // CHUNK + 1):
+        st = make_states(CHUNK, description, schedule_ctrl=schedule_ctrl, seed=seed + c, **kwargs)
+        a, b = max(lo, c * CHUNK) - c * CHUNK, min(hi, (c + 1) * CHUNK) - c * CHUNK
+        parts.append(st.slice(a, b))
+    return SyntheticStates(**{f.name: np.concatenate([getattr(p, f.name) for p in parts]) for f in dataclasses.fields(SyntheticStates)})

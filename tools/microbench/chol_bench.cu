@@ -312,6 +312,116 @@ __device__ __noinline__ void chol_dmma(double* psi, double* rdiag, double* blk, 
   PH_END(N6 - 1);
 }
 
+
+// ---------------------------------------------------------------- V9: FP64 tensor-core (DMMA m8n8k4) update AND triangular solve.
+// 8 x 8 tiles.  Per block column J:  (1) every warp updates its tiles (I, J), I >= J, with DMMA over the factored columns;
+// (2) ONE warp factors the 8 x 8 diagonal tile cooperatively -- lane (g, q) holds columns q and q + 4 of row g of [S | I],
+// eight elimination steps turn it into [L^T | L^-1] with shuffles only (nobody factors the block redundantly);
+// (3) every warp multiplies its tiles below the diagonal by L^-T with two DMMAs per tile.  3 barriers per 8 columns.
+template <int N6>
+__device__ __noinline__ void chol_dmma2(double* psi, double* rdiag, double* blk, double* linv, int* flag) {
+  constexpr int NB = (N6 + 7) / 8;
+  constexpr int NW = (N6 + 31) / 32;
+  constexpr int TPW = (NB + NW - 1) / NW;
+  const int i = threadIdx.x, lane = i & 31, wid = i >> 5, g = lane >> 2, q = lane & 3;
+  if (i == 0) *flag = 0;
+#pragma unroll 1
+  for (int J = 0; J < NB; ++J) {
+    const int j0 = 8 * J;
+    // ---- (1) left-looking update of block column J
+    {
+      double d[TPW][2];
+      const double* ap[TPW];
+      const int brow = j0 + g < N6 ? j0 + g : N6 - 1;
+      const double* bp = psi + prow(brow) + q;
+#pragma unroll
+      for (int s = 0; s < TPW; ++s) {
+        const int arow = 8 * (J + wid + s * NW) + g;
+        ap[s] = psi + prow(arow < N6 ? arow : N6 - 1) + q;
+        d[s][0] = d[s][1] = 0.0;
+      }
+#pragma unroll 2
+      for (int k0 = 0; k0 < j0; k0 += 4) {
+        const double b = bp[k0];
+#pragma unroll
+        for (int s = 0; s < TPW; ++s) {
+          if (J + wid + s * NW < NB) {     // warp-uniform
+            const double a = ap[s][k0];
+            dmma884(d[s][0], d[s][1], a, b);
+          }
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < TPW; ++s) {
+        const int I = J + wid + s * NW;
+        if (I < NB) {
+          const int row = 8 * I + g;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = j0 + 2 * q + e;
+            if (I == J) {
+              // diagonal tile: full symmetric 8 x 8 into the side buffer, identity beyond the matrix
+              double v;
+              if (row < N6 && col < N6) v = (col <= row ? psi[prow(row) + col] : psi[prow(col) + row]) - d[s][e];
+              else v = (row == col) ? 1.0 : 0.0;
+              blk[8 * g + 2 * q + e] = v;
+            } else if (row < N6) {
+              psi[prow(row) + col] -= d[s][e];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- (2) diagonal tile: [S | I] -> [L^T | L^-1], one warp
+    if (wid == 0) {
+      double s0 = blk[8 * g + q], s1 = blk[8 * g + q + 4];
+      double i0 = (g == q) ? 1.0 : 0.0, i1 = (g == q + 4) ? 1.0 : 0.0;
+      bool bad = false;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const double piv = __shfl_sync(kFull, (c < 4) ? s0 : s1, 4 * c + (c & 3));
+        const double m = __shfl_sync(kFull, (c < 4) ? s0 : s1, (lane & ~3) | (c & 3));
+        double dd = piv;
+        if (!(dd > 0.0)) { bad = true; dd = 1e-300; }
+        const double rd = rsqrt(dd);
+        const double p0 = __shfl_sync(kFull, s0, 4 * c + q) * rd, p1 = __shfl_sync(kFull, s1, 4 * c + q) * rd;
+        const double r0 = __shfl_sync(kFull, i0, 4 * c + q) * rd, r1 = __shfl_sync(kFull, i1, 4 * c + q) * rd;
+        const double t = m * rd;
+        if (g == c) { s0 = p0; s1 = p1; i0 = r0; i1 = r1; }
+        else if (g > c) { s0 = fma(-t, p0, s0); s1 = fma(-t, p1, s1); i0 = fma(-t, r0, i0); i1 = fma(-t, r1, i1); }
+      }
+      // L^T[g][c] = L[c][g]: strictly lower entries of L go back into Psi, 1 / L[g][g] = L^-1[g][g] into rdiag
+      if (q > g && j0 + q < N6) psi[prow(j0 + q) + j0 + g] = s0;
+      if (q + 4 > g && j0 + q + 4 < N6) psi[prow(j0 + q + 4) + j0 + g] = s1;
+      if (q == g && j0 + g < N6) rdiag[j0 + g] = i0;
+      if (q + 4 == g && j0 + g < N6) rdiag[j0 + g] = i1;
+      linv[8 * g + q] = i0;
+      linv[8 * g + q + 4] = i1;
+      if (bad && lane == 0) *flag = 1;
+    }
+    __syncthreads();
+    // ---- (3) tiles below the diagonal: X = C' L^-T  (B fragment: B[k][n] = L^-1[n][k])
+    {
+      const double b0 = linv[8 * g + q], b1 = linv[8 * g + 4 + q];
+#pragma unroll
+      for (int s = 0; s < TPW; ++s) {
+        const int I = J + wid + s * NW;
+        if (I > J && I < NB) {
+          const int row = 8 * I + g;
+          double* rp = psi + prow(row < N6 ? row : N6 - 1) + j0;
+          const double a0 = rp[q], a1 = rp[4 + q];
+          double x0 = 0.0, x1 = 0.0;
+          dmma884(x0, x1, a0, b0);
+          dmma884(x0, x1, a1, b1);
+          if (row < N6) { rp[2 * q] = x0; rp[2 * q + 1] = x1; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <int N6, int VARIANT>
 __global__ void __launch_bounds__(((N6 + 31) / 32) * 32, 8)
 bench_kernel(const double* __restrict__ a_dense, double* __restrict__ l_out, long long* __restrict__ cycles, int reps) {
@@ -334,6 +444,7 @@ bench_kernel(const double* __restrict__ a_dense, double* __restrict__ l_out, lon
     if (VARIANT == 4) chol_panel<N6, 8, 1>(psi, rdiag, blk, flag);
     if (VARIANT == 5) chol_panel<N6, 2, 4>(psi, rdiag, blk, flag);
     if (VARIANT == 6) chol_dmma<N6>(psi, rdiag, blk, flag);
+    if (VARIANT == 9) chol_dmma2<N6>(psi, rdiag, blk, reinterpret_cast<double*>(flag) + 2, flag);
     total += clock64() - t0;
     __syncthreads();
   }
@@ -349,7 +460,7 @@ bench_kernel(const double* __restrict__ a_dense, double* __restrict__ l_out, lon
 template <int N6, int VARIANT>
 void run(const char* name, const double* d_a, const std::vector<double>& l_ref, double* d_l, long long* d_cyc) {
   const int nt = ((N6 + 31) / 32) * 32;
-  const size_t smem = (N6 * (N6 + 1) / 2 + 64 + N6 + 64 + 2) * sizeof(double) + (N6 == 60 ? 4600 : 0);   // ~23 KB at N6=60, like the solver
+  const size_t smem = (N6 * (N6 + 1) / 2 + 64 + N6 + 64 + 2) * sizeof(double) + (N6 == 60 ? 4600 : 1024);   // ~23 KB at N6=60, like the solver
   cudaFuncSetAttribute(bench_kernel<N6, VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(bench_kernel<N6, VARIANT>, cudaFuncAttributePreferredSharedMemoryCarveout, 90);
   const int reps = 20;
@@ -820,6 +931,7 @@ void run_all() {
   run<N6, 4>("panel W=8 unroll 1", d_a, l, d_l, d_cyc);
   run<N6, 5>("panel W=2 unroll 4", d_a, l, d_l, d_cyc);
   run<N6, 6>("DMMA m8n8k4 update, W=8", d_a, l, d_l, d_cyc);
+  run<N6, 9>("DMMA update + shuffle diag + DMMA trsm", d_a, l, d_l, d_cyc);
   run_sq<N6, 0>("square LD=N+2, LDS.128, W=4 u2", d_a, l, d_l, d_cyc);
   run_sq<N6, 1>("square LD=N+2, LDS.128, W=6 u2", d_a, l, d_l, d_cyc);
   run_sq<N6, 2>("square LD=N+2, LDS.128, W=4 u4", d_a, l, d_l, d_cyc);
@@ -842,6 +954,7 @@ void run_all() {
 int main() {
   run_all<60>();
   run_all<30>();
+  run_all<120>();
 
   return 0;
 }

@@ -8,22 +8,24 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(REPO, "robot-gym_b200")); sys.path.insert(0, REPO)
 import numpy as np, torch
 from robot_gym import cuda as rg
-from robot_gym.model.robots.descriptions import GHOST
+from robot_gym.model.robots.descriptions import GHOST, with_gait
 from robot_gym.util import synthetic
 from oracle import c_oracle, convex_mpc
 
 def main():
     sizes = [int(a) for a in sys.argv[1:]] or [4096, 65536]
     ctrl = GHOST.GetCtrlConstants()
-    for horizon in (10,):
+    gait = os.environ.get("RG_PERF_GAIT", "trot")
+    desc = GHOST if gait == "trot" else with_gait(GHOST, gait)
+    for horizon in [int(h) for h in os.environ.get("RG_PERF_H", "10").split(",")]:
         p = rg.default_mpc_params(ctrl.MPC_BODY_MASS, ctrl.MPC_BODY_INERTIA, ctrl.MPC_BODY_HEIGHT, horizon)
         for kv in filter(None, os.environ.get("RG_PERF_PARAMS", "").split(",")):     # e.g. ipm_tol=1e-4,cold_start_rounds=0
             k, v = kv.split("=")
             setattr(p, k, type(getattr(p, k))(float(v)))
-        ws = rg.MpcWorkspace(p)
+        ws = rg.MpcWorkspace(p, max_envs=max(sizes))
         for n in sizes:
-            for all_stance in (False, True):
-                st = synthetic.make_states(n, GHOST, all_stance=all_stance)
+            for all_stance in (False, True)[:1 if os.environ.get("RG_PERF_NO_ALLSTANCE") else 2]:
+                st = synthetic.make_states(n, desc, schedule_ctrl=desc.GetCtrlConstants(), all_stance=all_stance)
                 t = lambda a: torch.from_numpy(a).cuda()
                 args = (t(st.com_velocity_body), t(st.base_rpy), t(st.base_rpy_rate), t(st.planned_contacts), t(st.foot_positions_base), t(st.command))
                 f = torch.empty((n, 12), dtype=torch.float32, device="cuda"); info = torch.empty((n, 4), dtype=torch.int32, device="cuda")
@@ -39,7 +41,7 @@ def main():
                 m = min(n, 512)
                 ref, _, _ = c_oracle.solve_batch(convex_mpc.MpcParams(horizon=horizon), st.slice(0, m), ctrl.MPC_BODY_HEIGHT, n_threads=os.cpu_count())
                 err = (np.abs(fo[:m] - ref).max(axis=1) / np.maximum(1, np.abs(ref).max(axis=1))).max()
-                print(f"h={horizon} n={n} all_stance={all_stance}: {med:.3f} ms  {n/med*1e3:,.0f} solves/s | iters {inf[:,0].mean():.2f} polish {inf[:,1].mean():.2f} "
+                print(f"{gait} h={horizon} n={n} all_stance={all_stance}: {med:.3f} ms  {n/med*1e3:,.0f} solves/s | iters {inf[:,0].mean():.2f} polish {inf[:,1].mean():.2f} "
                       f"polished {np.mean((inf[:,2]&1)!=0):.4f} cold {np.mean((inf[:,2]&16)!=0):.3f} | worst rel err vs C oracle {err:.2e}")
 
 if __name__ == "__main__":
