@@ -321,6 +321,13 @@ typedef struct rg_controller_state {
   float* motor_torques;                  /* [N,12] */
   int32_t* solve_info;                   /* [N,4] or NULL */
   float* action;                         /* [N,60] */
+  /* optional torque consumer (all three NULL = not attached): when applied_motor_torques is given, the epilogue
+   * also evaluates the HYBRID motor model on the fresh command -- Robot.ApplyAction of the first of the
+   * ACTION_REPEAT physics ticks (robot.py:276-307, simple_motor.py:128-140) -- so a GPU physics step can consume
+   * torques without reading the [N,60] command back */
+  const float* motor_velocities;         /* [N,12] GetMotorVelocities convention, required with the consumer */
+  const float* motor_strength_ratios;    /* [N,12] RobotMotorModel._strength_ratios (simple_motor.py:52-60) or NULL = 1 */
+  float* applied_motor_torques;          /* [N,12] OUT: strength * PD-plus-feed-forward torque * MOTOR_DIRECTION */
 } rg_controller_state;
 
 int rg_control_step(const void* mpc_workspace, const void* robot_workspace, int n_env,
@@ -331,6 +338,13 @@ int rg_control_step(const void* mpc_workspace, const void* robot_workspace, int 
  * tau = -kp (q - q_des) - kd (qd - qd_des) + tau_ff ; no clipping (robot.py:40-45). */
 int rg_hybrid_motor_torque(int n_env, const float* action, const float* motor_angles,
                            const float* motor_velocities, float* motor_torques, void* stream);
+/* The same with the two factors Robot.ApplyAction applies around it (robot.py:276-307):
+ *   observed = strength_ratios * tau      (simple_motor.py:140; strength_ratios [N,12] or NULL = 1)
+ *   applied  = observed * MOTOR_DIRECTION (robot.py:291-292; from the robot workspace)
+ * Either output may be NULL.  One call per physics tick of Simulation.ApplyStepAction (core/simulation.py:175-179). */
+int rg_hybrid_motor_torque_ex(const void* robot_workspace, int n_env, const float* action, const float* motor_angles,
+                              const float* motor_velocities, const float* strength_ratios,
+                              float* observed_torques, float* applied_torques, void* stream);
 
 /* Diagnostic (synchronises the device): best-of-4 CUDA-core FMA throughput in TFLOP/s, fp32 or fp64,
  * the roofline denominator for the solve kernel (MEASURED_PEAKS.json has no CUDA-core peak). */

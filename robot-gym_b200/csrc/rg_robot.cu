@@ -439,8 +439,19 @@ __global__ void step_epilogue_kernel(const RgRobotDev* __restrict__ R, int n_env
   leg_torque(*R, leg, s.contact_forces + 3 * (size_t)idx, s.motor_angles + 3 * (size_t)idx, tau);
   float tf[3];
   for (int j = 0; j < 3; ++j) { tf[j] = (float)tau[j]; s.motor_torques[3 * (size_t)idx + j] = tf[j]; }
-  pack_leg(*R, leg, s.desired_leg_state[idx], s.swing_joint_valid[idx] != 0, s.swing_joint_angles + 3 * (size_t)idx, tf,
-           s.action + 15 * (size_t)idx);
+  float cmd[15];
+  pack_leg(*R, leg, s.desired_leg_state[idx], s.swing_joint_valid[idx] != 0, s.swing_joint_angles + 3 * (size_t)idx, tf, cmd);
+  for (int i = 0; i < 15; ++i) s.action[15 * (size_t)idx + i] = cmd[i];
+  if (s.applied_motor_torques) {
+    // torque consumer attached: HYBRID motor model on the command just packed (first physics tick of the step)
+    for (int j = 0; j < 3; ++j) {
+      const size_t m = 3 * (size_t)idx + j;
+      const float* a = cmd + 5 * j;
+      float tau = -1.f * (a[1] * (s.motor_angles[m] - a[0])) - a[3] * (s.motor_velocities[m] - a[2]) + a[4];
+      if (s.motor_strength_ratios) tau *= s.motor_strength_ratios[m];
+      s.applied_motor_torques[m] = tau * (float)R->motor_direction[3 * leg + j];
+    }
+  }
 }
 
 __global__ void hybrid_motor_kernel(int n, const float* __restrict__ action, const float* __restrict__ q,
@@ -450,6 +461,19 @@ __global__ void hybrid_motor_kernel(int n, const float* __restrict__ action, con
   const float* a = action + 5 * (size_t)idx;
   // -1 * (kp * (q - q_des)) - kd * (qd - qd_des) + tau_ff   (simple_motor.py:138-139)
   tau[idx] = -1.f * (a[1] * (q[idx] - a[0])) - a[3] * (qd[idx] - a[2]) + a[4];
+}
+
+__global__ void hybrid_motor_ex_kernel(const RgRobotDev* __restrict__ R, int n, const float* __restrict__ action,
+                                       const float* __restrict__ q, const float* __restrict__ qd,
+                                       const float* __restrict__ strength, float* __restrict__ observed,
+                                       float* __restrict__ applied) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over N*12 motors
+  if (idx >= n) return;
+  const float* a = action + 5 * (size_t)idx;
+  float tau = -1.f * (a[1] * (q[idx] - a[0])) - a[3] * (qd[idx] - a[2]) + a[4];
+  if (strength) tau *= strength[idx];                      // simple_motor.py:140
+  if (observed) observed[idx] = tau;
+  if (applied) applied[idx] = tau * (float)R->motor_direction[idx % RG_NUM_MOTORS];   // robot.py:291-292
 }
 
 // ------------------------------------------------------------------------------------ host: setup
@@ -688,6 +712,16 @@ extern "C" int rg_hybrid_motor_torque(int n_env, const float* action, const floa
   return rg_check_cuda(cudaGetLastError(), "hybrid_motor_kernel launch");
 }
 
+extern "C" int rg_hybrid_motor_torque_ex(const void* ws, int n_env, const float* action, const float* q, const float* qd,
+                                         const float* strength, float* observed, float* applied, void* stream) {
+  if (n_env == 0) return RG_OK;   // empty batch: nothing to validate, nothing to launch
+  RG_REQUIRE(ws && action && q && qd && (observed || applied) && n_env >= 0, "rg_hybrid_motor_torque_ex");
+  hybrid_motor_ex_kernel<<<grid_for(12 * n_env, 256), 256, 0, (cudaStream_t)stream>>>((const RgRobotDev*)ws, 12 * n_env, action, q, qd,
+                                                                                       strength, observed, applied);
+  rg_count_launch();
+  return rg_check_cuda(cudaGetLastError(), "hybrid_motor_ex_kernel launch");
+}
+
 extern "C" int rg_control_step(const void* mpc_ws, const void* robot_ws, int n_env, const rg_controller_state* s, void* stream) {
   if (n_env == 0) return RG_OK;   // empty batch: nothing to validate, nothing to launch
   RG_REQUIRE(mpc_ws && robot_ws && s && n_env >= 0, "rg_control_step");
@@ -698,6 +732,7 @@ extern "C" int rg_control_step(const void* mpc_ws, const void* robot_ws, int n_e
              "rg_control_step state");
   RG_REQUIRE(s->desired_leg_state && s->leg_state && s->normalized_phase && s->mpc_contact_state && s->swing_foot_target &&
              s->com_velocity_body && s->contact_forces && s->motor_torques && s->action, "rg_control_step outputs");
+  RG_REQUIRE(!s->applied_motor_torques || s->motor_velocities, "rg_control_step torque consumer (motor_velocities)");
   cudaStream_t st = (cudaStream_t)stream;
   step_prologue_kernel<<<grid_for(n_env, 128), 128, 0, st>>>((const RgRobotDev*)robot_ws, n_env, *s);
   rg_count_launch();

@@ -41,7 +41,8 @@ def test_struct_layouts_match_header_sizes(rg_lib):
     # sizes computed from the header's field lists (8-byte aligned doubles, 4-byte ints)
     assert ctypes.sizeof(rg.MpcParams) == 8 + 72 + 4 + 4 + 8 + 104 + 8 + 32 + 8 + 8 + 8 + 8 + 8 + 4 + 4 + 4 + 4 + 4 + 4
     assert ctypes.sizeof(rg.LegChain) == 8 * (9 + 27 + 9 + 3 + 2)
-    assert ctypes.sizeof(rg.ControllerState) == 8 * 29
+    assert ctypes.sizeof(rg.ControllerState) == 8 * 32
+    assert ctypes.sizeof(rg.MpcIo) == 8 * 12 + 8
 
 
 def test_default_params_follow_motion_imitation_defaults(rg_lib):
