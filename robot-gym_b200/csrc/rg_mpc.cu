@@ -1696,7 +1696,8 @@ int launch_h(const RgMpcDev* ws, int n_env, const rg_mpc_io& io, int two_kernel,
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = n_env < sms * 2 ? n_env : sms * 2;
+    const int slots = sms * Cfg<H>::MIN_BLOCKS;          // as many CTAs as fit at once: an empty queue costs one wave of exits
+    const int grid = n_env < slots ? n_env : slots;
     mpc_fallback_kernel<H><<<grid, Cfg<H>::NT, smem, stream>>>(ws, scratch, n_env, io);
     rg_count_launch();
     return rg_check_cuda(cudaGetLastError(), "mpc_fallback_kernel launch");

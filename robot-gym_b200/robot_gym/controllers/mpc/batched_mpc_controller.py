@@ -69,10 +69,16 @@ class BatchedMPCController(Controller):
         ``[N]`` float64 tensor (Simulation.GetTimeSinceReset, core/simulation.py:141-142).
         ``warm_start``: seed each stance QP with the active set the same env verified one control step
         earlier (``rg_mpc_build_solve_warm``); the optimum is unique, so the forces do not depend on it."""
-        super().__init__(robot, get_time_since_reset)
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedMPCController needs a CUDA device (no CPU fallback)")
         rg.load()
+        self._adapter = None
+        if not hasattr(robot, "num_envs"):
+            # a stock (PyBullet-backed) Robot, as Simulation.build_world passes it (core/simulation.py:117):
+            # N = 1 behind the batched getter surface
+            from robot_gym.model.robots.pybullet_adapter import PyBulletRobotAdapter
+            robot = self._adapter = PyBulletRobotAdapter(robot)
+        super().__init__(robot, get_time_since_reset)
         self._constants = robot.GetCtrlConstants()
         self.device = torch.device(getattr(robot, "device", "cuda"))
         self.num_envs = int(getattr(robot, "num_envs", 1))
@@ -179,6 +185,8 @@ class BatchedMPCController(Controller):
         swing (latch = current feet, joint-angle store cleared) and stance state are re-armed.
         ``env_ids`` (LongTensor) restricts the reset to a subset of envs."""
         sel = slice(None) if env_ids is None else env_ids
+        if self._adapter is not None:
+            self._adapter.refresh()
         self.reset_time[sel] = self._clock()[sel]
         self.vel_window[sel] = 0
         self.vel_window_sum[sel] = 0
@@ -264,9 +272,33 @@ class BatchedMPCController(Controller):
                 cache[field] = (t.data_ptr(), t.shape, t.dtype)
             cache[field + "_ref"] = t          # keep the storage alive until the kernels have consumed it
 
+    def attach_torque_consumer(self, motor_velocities_getter, strength_ratios=None, applied_motor_torques=None):
+        """Fuse the HYBRID motor model of the first physics tick into the step's epilogue:
+        ``applied_motor_torques`` [N,12] = strength_ratios * (-kp (q - q_des) - kd (qd - qd_des) + tau) *
+        MOTOR_DIRECTION (simple_motor.py:128-140, robot.py:291-292) is written by the same launch that packs the
+        command, so a GPU physics step never reads the [N,60] command back.  Returns the output tensor."""
+        n, dev, f32 = self.num_envs, self.device, torch.float32
+        if applied_motor_torques is None:
+            applied_motor_torques = torch.zeros((n, 12), dtype=f32, device=dev)
+        self.applied_motor_torques = applied_motor_torques
+        self._motor_velocities_getter = motor_velocities_getter
+        self._strength_ratios = strength_ratios
+        self._state.applied_motor_torques = rg._ptr(applied_motor_torques, f32, (12,), n=n, device=dev)
+        self._state.motor_strength_ratios = rg._ptr(strength_ratios, f32, (12,), allow_none=True, n=n, device=dev)
+        return applied_motor_torques
+
     def step(self):
+        if self._adapter is not None:
+            self._adapter.refresh()
         torch.sub(self._clock(), self.reset_time, out=self.time_since_reset)
         self._refresh_inputs()
+        if getattr(self, "_motor_velocities_getter", None) is not None:
+            qd = self._motor_velocities_getter()
+            key = (qd.data_ptr(), qd.shape, qd.dtype)
+            if self._input_cache.get("motor_velocities") != key:
+                self._state.motor_velocities = rg._ptr(qd, torch.float32, (12,), n=self.num_envs, device=self.device)
+                self._input_cache["motor_velocities"] = key
+            self._input_cache["motor_velocities_ref"] = qd
         with torch.cuda.device(self.device):
             rg.check(rg.load().rg_control_step(self._mpc_ws.ptr, self._robot_ws.ptr, self.num_envs,
                                                ctypes.byref(self._state), rg.current_stream_ptr()))
