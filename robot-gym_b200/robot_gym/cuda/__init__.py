@@ -187,8 +187,11 @@ def _ptr(t, dtype, shape_tail=None, allow_none=False, n=None, device=None, align
         raise ValueError(f"expected shape [N,{','.join(map(str, shape_tail))}], got {tuple(t.shape)}")
     if n is not None and (t.dim() == 0 or t.shape[0] != n):
         raise ValueError(f"expected {n} rows (one per env), got shape {tuple(t.shape)}")
-    if device is not None and t.device != torch.device(device):
-        raise ValueError(f"tensor lives on {t.device}, the call runs on {torch.device(device)}")
+    if device is not None:
+        want = torch.device(device)
+        want_index = torch.cuda.current_device() if want.index is None else want.index
+        if t.device.type != want.type or t.device.index != want_index:
+            raise ValueError(f"tensor lives on {t.device}, the call runs on {want.type}:{want_index}")
     if align > 1 and t.data_ptr() % align:
         raise ValueError(f"tensor storage must be {align}-byte aligned")
     return c_void_p(t.data_ptr())

@@ -49,7 +49,7 @@ class BatchedRobotGymEnv:
         return torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
 
     def get_observation(self):
-        """Default proprioceptive observation [N, 46]: rpy, body-frame angular velocity, motor angles, motor
+        """Default proprioceptive observation [N, 37]: rpy, body-frame angular velocity, motor angles, motor
         velocities, body-frame COM velocity estimate, foot contacts."""
         r, c = self._simulation.robot, self._simulation.controller
         return torch.cat([r.GetBaseRollPitchYaw(), r.GetBaseRollPitchYawRate(), r.GetMotorAngles(), r.GetMotorVelocities(),

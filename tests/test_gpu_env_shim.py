@@ -36,7 +36,7 @@ def test_env_shim_4096_envs_100_steps_equals_the_unshimmed_controller(rg_lib, cu
     shadow = BatchedMPCController(sim.robot, sim.GetTimeSinceReset)
     obs = env.reset()
     shadow.reset()
-    assert obs.shape == (n, 46) and obs.is_cuda
+    assert obs.shape == (n, 37) and obs.is_cuda
     gen = torch.Generator(device="cpu").manual_seed(3)
     n_resets = 0
     for k in range(steps):
@@ -48,7 +48,7 @@ def test_env_shim_4096_envs_100_steps_equals_the_unshimmed_controller(rg_lib, cu
         t_before = sim.GetTimeSinceReset().clone()
         obs, reward, done, info = env.step(act)
         assert torch.equal(env.last_action, expect), k
-        assert obs.shape == (n, 46) and reward.shape == (n,) and done.shape == (n,) and done.dtype == torch.bool
+        assert obs.shape == (n, 37) and reward.shape == (n,) and done.shape == (n,) and done.dtype == torch.bool
         assert torch.isfinite(obs).all() and torch.isfinite(env.last_action).all()
         fell = done.nonzero().flatten()
         alive = (~done).nonzero().flatten()
