@@ -462,6 +462,9 @@ def _latency_table(torch, rg, Controller, RobotBatch, synthetic, desc, dev):
             for key, warm in (("cold", False), ("warm", True)):
                 robot = RobotBatch(desc, synthetic.make_states_sharded(0, n, desc), device=dev)
                 ctl = Controller(robot, robot.GetTimeSinceReset, warm_start=warm)
+                # the controller latched reset_time = clock at construction, which would freeze every env at gait time 0
+                # (all four legs in stance, the hardest pattern): run on the states' own gait clocks (t0 ~ U(0, 0.5 s))
+                ctl.reset_time.zero_()
                 ctl.command.copy_(torch.from_numpy(synthetic.make_states_sharded(0, n, desc).command).to(dev))
                 for _ in range(20):
                     ctl.step()

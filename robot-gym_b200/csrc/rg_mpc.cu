@@ -93,18 +93,39 @@ struct Cfg {
 #ifndef RG_MIN_BLOCKS_H5
 #define RG_MIN_BLOCKS_H5 24
 #endif
+// Linear algebra behind the Newton / active-set systems:  horizons >= RG_RICCATI_MIN_H factorise Psi by a backward
+// Riccati sweep over the horizon (O(h) work and storage: riccati_factor / riccati_solve), shorter ones by the dense
+// packed Cholesky (O(h^3), but 60 rows keep 64 threads busy and the panel routine is faster up to h = 10; measured
+// in profiles/r02_riccati_vs_cholesky.md).
+#ifndef RG_RICCATI_MIN_H
+#define RG_RICCATI_MIN_H 20
+#endif
+#ifndef RG_MIN_BLOCKS_H20
+#define RG_MIN_BLOCKS_H20 4
+#endif
+  static constexpr bool RICCATI = H >= RG_RICCATI_MIN_H;
   static constexpr int CHOL_W = (H == 10) ? RG_CHOL_W_H10 : 4;
-  static constexpr int MIN_BLOCKS = H <= 5 ? RG_MIN_BLOCKS_H5 : (H <= 10 ? RG_MIN_BLOCKS_H10 : 2);
+  static constexpr int MIN_BLOCKS = H <= 5 ? RG_MIN_BLOCKS_H5 : (H <= 10 ? RG_MIN_BLOCKS_H10 : (RICCATI ? RG_MIN_BLOCKS_H20 : 2));
 };
 
-template <int H>
+template <int H, bool RIC = Cfg<H>::RICCATI>
 struct Smem {
-  __align__(16) double psi[Cfg<H>::NPSI];   // lower triangle, row-major, rows padded to even length (prow)
-  double kinv_ang[Cfg<H>::NKA];    // K^-1 angular block, packed, index a = 3 j + c
+  // dense path: Psi and its Cholesky factor
+  __align__(16) double psi[RIC ? 2 : Cfg<H>::NPSI];   // lower triangle, row-major, rows padded to even length (prow)
+  double kinv_ang[RIC ? 1 : Cfg<H>::NKA];    // K^-1 angular block, packed, index a = 3 j + c
+  double rdiag[RIC ? 1 : Cfg<H>::N6];
+  // Riccati path (see riccati_factor): per stage P_{t+1} Gam (12 x 6), J_t, N_t (6 x 6), and the sweep's scratch
+  __align__(16) double fac_pg[RIC ? H : 1][72];
+  __align__(16) double fac_j[RIC ? H : 1][36];
+  __align__(16) double fac_n[RIC ? H : 1][36];
+  __align__(16) double pm[RIC ? 144 : 2];      // P_{t+1}: full symmetric storage, row-major 12 x 12, order (pi; sigma)
+  __align__(16) double pm2[RIC ? 144 : 2];     // P_{t+1} - PG N PG^T before the time update
+  __align__(16) double m6[RIC ? 6 : 1][36];    // 6 x 6 scratch matrices: D, S, U = D S, Y, Y^-1, G
+  __align__(16) double t1[RIC ? 72 : 2];       // PG N
+  double rvec[RIC ? H * 6 : 1];                // r_t of the backward sweep of the current solve
   double gt[H * 6];                // g~ : gradient in acceleration space
   double avec[H * 6];              // W u, right-hand sides and Woodbury solutions
   double kvec[H * 6];              // K (W u)
-  double rdiag[Cfg<H>::N6];
   __align__(16) double blk44[36];  // updated diagonal block of the current Cholesky panel (4x4 or 6x6)
   double bang[4][9];               // A_leg = I_world^-1 [r_leg]x
   double k2ang[9];
@@ -223,8 +244,8 @@ __device__ __forceinline__ double quad_sum(double v) {   // sum over the 4 legs 
 // __noinline__: one copy of the code, called from every phase of the solver.
 // j_begin (a multiple of 4): columns before it already hold the factor and are kept -- a matrix that
 // changed only in rows/columns >= j_begin has the same leading factor columns (left-looking order).
-template <int H>
-__device__ RG_HEAVY_INLINE void cholesky_rows(Smem<H>& sm, int j_begin) {
+template <int H, class SM>
+__device__ RG_HEAVY_INLINE void cholesky_rows(SM& sm, int j_begin) {
   constexpr int N6 = Cfg<H>::N6;
   const int i = threadIdx.x;
   const bool row_ok = i < N6;
@@ -361,8 +382,8 @@ __device__ RG_HEAVY_INLINE void cholesky_rows(Smem<H>& sm, int j_begin) {
 // Generic W-wide panel variant of cholesky_rows (compiler-scheduled update loop, right-looking factorisation of the
 // W x W diagonal block in registers).  RG_CHOL_W = 6 matches the 6 x 6 time blocks of Psi: 10 panels instead of 15
 // at h = 10, and a partial refactorisation can restart at ANY time block (6 t_begin is always a panel boundary).
-template <int H, int W>
-__device__ RG_HEAVY_INLINE void cholesky_rows_w(Smem<H>& sm, int j_begin) {
+template <int H, int W, class SM>
+__device__ RG_HEAVY_INLINE void cholesky_rows_w(SM& sm, int j_begin) {
   constexpr int N6 = Cfg<H>::N6;
   static_assert(N6 % W == 0 && W * W <= 36, "panel width must divide 6h and fit the side buffer");
   const int i = threadIdx.x;
@@ -449,8 +470,8 @@ __device__ RG_HEAVY_INLINE void cholesky_rows_w(Smem<H>& sm, int j_begin) {
 // 8.7-9.3k cycles per solve alone on an SM against 14.8k for one-pivot-per-step with strided rows.)
 // T(i) mod 16 is a permutation over the even and over the odd rows of 16 consecutive lanes, so the
 // per-column loads stay bank-conflict free with this ownership too.
-template <int H>
-__device__ RG_HEAVY_INLINE void tri_solve_warp0(Smem<H>& sm) {
+template <int H, class SM>
+__device__ RG_HEAVY_INLINE void tri_solve_warp0(SM& sm) {
   constexpr int N6 = Cfg<H>::N6;
   constexpr int RPL = Cfg<H>::RPL;
   constexpr int NL = N6 / RPL;
@@ -563,6 +584,313 @@ __device__ __forceinline__ void psi_build_rows(Smem<H>& sm, const RgMpcDev* __re
       else if (d == c) v += ws->kinv_lin[c - 3][tri(j, j)];
       dst[d] = v;
     }
+  }
+}
+
+
+// =====================================================================================================================
+// State-space (Riccati) linear algebra, used for long horizons (Cfg<H>::RICCATI).
+//
+// Every system of the solver has the form  Psi v = b,  Psi = K^-1 + blkdiag_t(D_t)  (6h x 6h).  K is the Hessian, in
+// acceleration space, of the tracking cost of the linear system
+//     x_{i+1} = Phi x_i + Gam a_i,   x = (pi; sigma) in R^12,   sigma_i = sum_{j<i} a_j,   pi_i = sum_{j<i} (i-j-1/2) a_j,
+//     Phi = [[I, I], [0, I]],   Gam = [I/2; I],   1/2 a^T K a = sum_{i=1..h} 1/2 x_i^T Q x_i,   Q = blkdiag(K2, K1),
+// so with a = K^-1 v the equation is the two-point boundary value problem
+//     a_t = b_t - D_t v_t,   v_t = Gam^T lam_{t+1},   lam_i = Q x_i + Phi^T lam_{i+1},   x_0 = 0,  lam_{h+1} = 0,
+// which the backward Riccati sweep  lam_i = P_i x_i + p_i  factorises in O(h) operations on 6 x 6 / 12 x 12 matrices:
+//     P_h = Q;   for t = h-1 .. 0:   PG = P_{t+1} Gam,   S = Gam^T PG,   J_t = (I + S D_t)^-1 = S (S + S D_t S)^-1,
+//                                    N_t = D_t J_t,   P_t = Q + Phi^T (P_{t+1} - PG N_t PG^T) Phi.
+// Neither K^-1 nor any 6h x 6h matrix is formed: 144 h doubles of factors instead of 18 h^2 (23 KB instead of 73 KB of
+// shared memory at h = 20).  Y = S + S D S is symmetric positive definite (S is: every acceleration channel carries a
+// velocity or a position weight, rg_mpc_setup checks it) whatever the rank of D_t, so its inverse is taken by 3 x 3
+// blocks in closed form -- no pivoting, no square roots.  Phi and Gam consist of 0, 1/2 and 1: the time update of P and
+// the products with Gam are additions.
+//
+// One warp runs the sweep.  Every step is spread over the lanes so that a lane computes one or two 6-term dot products
+// (lane (r, cp) = row r, columns 2 cp and 2 cp + 1 of a 6 x 6 product; 128-bit shared-memory loads), results go through
+// shared memory, __syncwarp between steps: about 400 warp instructions per stage.
+// =====================================================================================================================
+enum { RM_D = 0, RM_S = 1, RM_U = 2, RM_Y = 3, RM_YI = 4, RM_G = 5 };
+
+__device__ __forceinline__ double2 ldd2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// out[r][2cp..2cp+1] = add[r][..] + sum_k a[r][k] b[k][..]  for the 6 x 6 row-major matrices a, b (add may be null)
+__device__ __forceinline__ double2 row_times_cols(const double* __restrict__ a, const double* __restrict__ b, int r, int cp) {
+  const double2 a01 = ldd2(a + 6 * r), a23 = ldd2(a + 6 * r + 2), a45 = ldd2(a + 6 * r + 4);
+  const double2 b0 = ldd2(b + 2 * cp), b1 = ldd2(b + 6 + 2 * cp), b2 = ldd2(b + 12 + 2 * cp);
+  const double2 b3 = ldd2(b + 18 + 2 * cp), b4 = ldd2(b + 24 + 2 * cp), b5 = ldd2(b + 30 + 2 * cp);
+  double2 o;
+  o.x = (a01.x * b0.x + a01.y * b1.x + a23.x * b2.x) + (a23.y * b3.x + a45.x * b4.x + a45.y * b5.x);
+  o.y = (a01.x * b0.y + a01.y * b1.y + a23.x * b2.y) + (a23.y * b3.y + a45.x * b4.y + a45.y * b5.y);
+  return o;
+}
+
+// inverse of a symmetric positive definite 3 x 3 matrix m = (00, 01, 02, 11, 12, 22) by cofactors; false if not SPD
+__device__ __forceinline__ bool inv3_spd(const double* m, double* o) {
+  const double c00 = m[3] * m[5] - m[4] * m[4], c01 = m[2] * m[4] - m[1] * m[5], c02 = m[1] * m[4] - m[2] * m[3];
+  const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+  const bool ok = det > 0.0 && m[0] > 0.0 && c00 > 0.0;
+  const double id = 1.0 / (ok ? det : 1.0);
+  o[0] = c00 * id; o[1] = c01 * id; o[2] = c02 * id;
+  o[3] = (m[0] * m[5] - m[2] * m[2]) * id; o[4] = (m[1] * m[2] - m[0] * m[4]) * id;
+  o[5] = (m[0] * m[3] - m[1] * m[1]) * id;
+  return ok;
+}
+
+// entry (r, c) of a symmetric 3 x 3 matrix packed (00, 01, 02, 11, 12, 22), by selects (no local-memory indexing)
+__device__ __forceinline__ double pick_sym3(const double* m, int r, int c) {
+  const int lo = r < c ? r : c, hi = r < c ? c : r;
+  const double row0 = hi == 0 ? m[0] : (hi == 1 ? m[1] : m[2]);
+  const double row1 = hi == 1 ? m[3] : m[4];
+  return lo == 0 ? row0 : (lo == 1 ? row1 : m[5]);
+}
+
+template <int H, class SM>
+__device__ RG_HEAVY_INLINE void riccati_factor(SM& sm) {
+  const int lane = threadIdx.x;   // caller guarantees threadIdx.x < 32
+  const int r6 = lane < 18 ? lane / 3 : 0, cp = lane < 18 ? lane - 3 * (lane / 3) : 0;      // 6 x 6 products: 18 lanes x 2 outputs
+  const int k12 = lane < 24 ? lane >> 1 : 0, ch = lane & 1;                                  // 12 x 6 products: 24 lanes x 3 outputs
+  // the (k, l), l <= k, entries of the 12 x 12 lower triangle this lane updates in step 8 (78 entries, <= 3 per lane)
+  int pk[3], pl[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int e = lane + 32 * i;
+    int k = 0;
+    while ((k + 1) * (k + 2) / 2 <= e) ++k;
+    pk[i] = e < 78 ? k : -1;
+    pl[i] = e - k * (k + 1) / 2;
+  }
+  for (int e = lane; e < 144; e += 32) {
+    const int r = e / 12, c = e - 12 * r;
+    double v = 0.0;
+    if (r < 3 && c < 3) v = sm.k2ang[3 * r + c];
+    else if (r == c) v = r < 6 ? sm.k2lin[r - 3] : sm.k1[r - 6];
+    sm.pm[e] = v;
+  }
+  if (lane == 0) sm.flag = 0;
+  __syncwarp();
+#pragma unroll 1
+  for (int t = H - 1; t >= 0; --t) {
+    double* __restrict__ pg = sm.fac_pg[t];
+    double* __restrict__ md = sm.m6[RM_D];
+    double* __restrict__ ms = sm.m6[RM_S];
+    // (1) PG = P Gam = P[:, :6] / 2 + P[:, 6:];  S = Gam^T P Gam = A/4 + (B + B^T)/2 + C;  D_t unpacked to 6 x 6
+    if (lane < 24) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) pg[6 * k12 + 3 * ch + c] = 0.5 * sm.pm[12 * k12 + 3 * ch + c] + sm.pm[12 * k12 + 6 + 3 * ch + c];
+    }
+    if (lane < 18) {
+      const double* __restrict__ nb = sm.nblk[t];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = 2 * cp + j;
+        ms[6 * r6 + c] = 0.25 * sm.pm[12 * r6 + c] + 0.5 * (sm.pm[12 * r6 + 6 + c] + sm.pm[12 * c + 6 + r6]) + sm.pm[12 * (6 + r6) + 6 + c];
+        md[6 * r6 + c] = r6 >= c ? nb[r6 * (r6 + 1) / 2 + c] : nb[c * (c + 1) / 2 + r6];
+      }
+    }
+    __syncwarp();
+    // (2) U = D S
+    if (lane < 18) {
+      const double2 o = row_times_cols(md, ms, r6, cp);
+      *reinterpret_cast<double2*>(sm.m6[RM_U] + 6 * r6 + 2 * cp) = o;
+    }
+    __syncwarp();
+    // (3) Y = S + S U   (symmetric positive definite)
+    if (lane < 18) {
+      double2 o = row_times_cols(ms, sm.m6[RM_U], r6, cp);
+      const double2 s0 = ldd2(ms + 6 * r6 + 2 * cp);
+      o.x += s0.x; o.y += s0.y;
+      *reinterpret_cast<double2*>(sm.m6[RM_Y] + 6 * r6 + 2 * cp) = o;
+    }
+    __syncwarp();
+    // (4) Y^-1 by 3 x 3 blocks, Y = [[A, B^T], [B, C]]:  G = B A^-1,  Sc = C - G B^T,
+    //     Y^-1 = [[A^-1 + G^T Sc^-1 G, -G^T Sc^-1], [-Sc^-1 G, Sc^-1]].   (4a) G: lanes 0..8, A^-1 redundantly
+    const double* __restrict__ my = sm.m6[RM_Y];
+    double* __restrict__ myi = sm.m6[RM_YI];
+    double* __restrict__ mg = sm.m6[RM_G];
+    double ai[6];
+    bool ok;
+    {
+      const double am[6] = {my[0], 0.5 * (my[1] + my[6]), 0.5 * (my[2] + my[12]), my[7], 0.5 * (my[8] + my[13]), my[14]};
+      ok = inv3_spd(am, ai);
+    }
+    const int gr = lane < 9 ? lane / 3 : 0, gc = lane < 9 ? lane - 3 * (lane / 3) : 0;
+    if (lane < 9) {
+      // B[r][k] = sym(Y[3 + r][k]);  A^-1 packed (00, 01, 02, 11, 12, 22): column gc = (ai[gc], ...)
+      const double b0 = 0.5 * (my[6 * (3 + gr)] + my[3 + gr]), b1 = 0.5 * (my[6 * (3 + gr) + 1] + my[6 + 3 + gr]),
+                   b2 = 0.5 * (my[6 * (3 + gr) + 2] + my[12 + 3 + gr]);
+      const double a0 = gc == 0 ? ai[0] : (gc == 1 ? ai[1] : ai[2]);
+      const double a1 = gc == 0 ? ai[1] : (gc == 1 ? ai[3] : ai[4]);
+      const double a2 = gc == 0 ? ai[2] : (gc == 1 ? ai[4] : ai[5]);
+      mg[3 * gr + gc] = b0 * a0 + b1 * a1 + b2 * a2;
+    }
+    __syncwarp();
+    // (4b) Sc and Sc^-1 redundantly in every lane; lanes 0..8 write -Sc^-1 G (block 21), lanes 9..17 Sc^-1 (block 22)
+    double sci[6];
+    {
+      double g[9], bmat[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) g[i] = mg[i];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) bmat[3 * r + c] = 0.5 * (my[6 * (3 + r) + c] + my[6 * c + 3 + r]);
+      double scm[6];
+      scm[0] = my[21] - (g[0] * bmat[0] + g[1] * bmat[1] + g[2] * bmat[2]);
+      scm[1] = 0.5 * (my[22] + my[27]) - (g[0] * bmat[3] + g[1] * bmat[4] + g[2] * bmat[5]);
+      scm[2] = 0.5 * (my[23] + my[33]) - (g[0] * bmat[6] + g[1] * bmat[7] + g[2] * bmat[8]);
+      scm[3] = my[28] - (g[3] * bmat[3] + g[4] * bmat[4] + g[5] * bmat[5]);
+      scm[4] = 0.5 * (my[29] + my[34]) - (g[3] * bmat[6] + g[4] * bmat[7] + g[5] * bmat[8]);
+      scm[5] = my[35] - (g[6] * bmat[6] + g[7] * bmat[7] + g[8] * bmat[8]);
+      ok = inv3_spd(scm, sci) && ok;
+      if (!ok && lane == 0) sm.flag = 1;
+      if (lane < 9) {
+        // -(Sc^-1 G)[gr][gc]
+        const double s0 = gr == 0 ? sci[0] : (gr == 1 ? sci[1] : sci[2]);
+        const double s1 = gr == 0 ? sci[1] : (gr == 1 ? sci[3] : sci[4]);
+        const double s2 = gr == 0 ? sci[2] : (gr == 1 ? sci[4] : sci[5]);
+        const double v = -(s0 * mg[gc] + s1 * mg[3 + gc] + s2 * mg[6 + gc]);
+        myi[6 * (3 + gr) + gc] = v;
+        myi[6 * gc + 3 + gr] = v;
+      } else if (lane < 18) {
+        const int r = (lane - 9) / 3, c = (lane - 9) - 3 * r;
+        myi[6 * (3 + r) + 3 + c] = pick_sym3(sci, r, c);
+      }
+    }
+    __syncwarp();
+    // (4c) block 11: A^-1 - G^T Y21   (Y21 = -Sc^-1 G just written)
+    if (lane < 9) {
+      const double a = pick_sym3(ai, gr, gc);
+      myi[6 * gr + gc] = a - (mg[gr] * myi[18 + gc] + mg[3 + gr] * myi[24 + gc] + mg[6 + gr] * myi[30 + gc]);
+    }
+    __syncwarp();
+    // (5) J = S Y^-1
+    if (lane < 18) {
+      const double2 o = row_times_cols(ms, myi, r6, cp);
+      *reinterpret_cast<double2*>(sm.fac_j[t] + 6 * r6 + 2 * cp) = o;
+    }
+    __syncwarp();
+    // (6) N = D J
+    if (lane < 18) {
+      const double2 o = row_times_cols(md, sm.fac_j[t], r6, cp);
+      *reinterpret_cast<double2*>(sm.fac_n[t] + 6 * r6 + 2 * cp) = o;
+    }
+    if (t == 0) break;                       // P_0 is never needed: x_0 = 0
+    __syncwarp();
+    // (7) T1 = PG N   (12 x 6; N symmetrised on the fly)
+    if (lane < 24) {
+      const double* __restrict__ nn = sm.fac_n[t];
+      double pr[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) pr[j] = pg[6 * k12 + j];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int cc = 3 * ch + c;
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) v = fma(pr[j], 0.5 * (nn[6 * j + cc] + nn[6 * cc + j]), v);
+        sm.t1[6 * k12 + cc] = v;
+      }
+    }
+    __syncwarp();
+    // (8) P' = P - T1 PG^T: lower triangle, mirrored into pm2
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int k = pk[i], l = pl[i];
+      if (k >= 0) {
+        const double2 t01 = ldd2(sm.t1 + 6 * k), t23 = ldd2(sm.t1 + 6 * k + 2), t45 = ldd2(sm.t1 + 6 * k + 4);
+        const double2 g01 = ldd2(pg + 6 * l), g23 = ldd2(pg + 6 * l + 2), g45 = ldd2(pg + 6 * l + 4);
+        const double v = sm.pm[12 * k + l] - ((t01.x * g01.x + t01.y * g01.y + t23.x * g23.x) + (t23.y * g23.y + t45.x * g45.x + t45.y * g45.y));
+        sm.pm2[12 * k + l] = v;
+        sm.pm2[12 * l + k] = v;
+      }
+    }
+    __syncwarp();
+    // (9) P_t = Q + Phi^T P' Phi:  A_t = A' + K2,  B_t = A' + B',  C_t = A' + B' + B'^T + C' + K1
+    if (lane < 18) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int r = r6, c = 2 * cp + j;
+        const double a = sm.pm2[12 * r + c], bb = sm.pm2[12 * r + 6 + c], bt = sm.pm2[12 * c + 6 + r], cc = sm.pm2[12 * (6 + r) + 6 + c];
+        double qa = 0.0, qc = 0.0;
+        if (r < 3 && c < 3) qa = sm.k2ang[3 * r + c];
+        else if (r == c) qa = sm.k2lin[r - 3];
+        if (r == c) qc = sm.k1[r];
+        sm.pm[12 * r + c] = a + qa;
+        sm.pm[12 * r + 6 + c] = a + bb;
+        sm.pm[12 * (6 + c) + r] = a + bb;
+        sm.pm[12 * (6 + r) + 6 + c] = a + bb + bt + cc + qc;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- Psi v = b with the Riccati factors; b / v in sm.avec; executed by warp 0 only ------------------------------
+// backward:  r_t = Gam^T (PG_t b_t + p_{t+1}),  w_t = b_t - N_t r_t,  p_t = Phi^T (p_{t+1} + PG_t w_t),  p_h = 0
+// forward :  v_t = J_t (PG_t^T Phi x_t + r_t),  a_t = b_t - D_t v_t,  x_{t+1} = Phi x_t + Gam a_t,  x_0 = 0
+// The 12-vectors p and x live in lanes 0..11 (pi part in lanes 0..5, sigma part in lanes 6..11), the 6-vectors in
+// lanes 0..5; everything moves by warp shuffles: no barrier and no shared-memory round trip on the chain.
+template <int H, class SM>
+__device__ RG_HEAVY_INLINE void riccati_solve(SM& sm) {
+  const int lane = threadIdx.x;   // caller guarantees threadIdx.x < 32
+  const int k12 = lane < 12 ? lane : 0, c6 = lane < 6 ? lane : 0;
+  double p = 0.0;
+#pragma unroll 1
+  for (int t = H - 1; t >= 0; --t) {
+    const double* __restrict__ pgk = sm.fac_pg[t] + 6 * k12;
+    const double* __restrict__ bt = sm.avec + 6 * t;
+    const double2 p01 = ldd2(pgk), p23 = ldd2(pgk + 2), p45 = ldd2(pgk + 4);
+    const double b0 = bt[0], b1 = bt[1], b2 = bt[2], b3 = bt[3], b4 = bt[4], b5 = bt[5];
+    const double bc = bt[c6];
+    const double z = (p01.x * b0 + p01.y * b1 + p23.x * b2) + (p23.y * b3 + p45.x * b4 + p45.y * b5) + p;   // (PG b + p)_k
+    const double zs = __shfl_down_sync(kFull, z, 6);
+    const double r = 0.5 * z + zs;                        // lanes 0..5: r_c = (Gam^T .)_c
+    if (lane < 6) sm.rvec[6 * t + lane] = r;
+    const double r0 = __shfl_sync(kFull, r, 0), r1 = __shfl_sync(kFull, r, 1), r2 = __shfl_sync(kFull, r, 2);
+    const double r3 = __shfl_sync(kFull, r, 3), r4 = __shfl_sync(kFull, r, 4), r5 = __shfl_sync(kFull, r, 5);
+    const double* __restrict__ nr = sm.fac_n[t] + 6 * c6;
+    const double2 n01 = ldd2(nr), n23 = ldd2(nr + 2), n45 = ldd2(nr + 4);
+    const double w = bc - ((n01.x * r0 + n01.y * r1 + n23.x * r2) + (n23.y * r3 + n45.x * r4 + n45.y * r5));
+    const double w0 = __shfl_sync(kFull, w, 0), w1 = __shfl_sync(kFull, w, 1), w2 = __shfl_sync(kFull, w, 2);
+    const double w3 = __shfl_sync(kFull, w, 3), w4 = __shfl_sync(kFull, w, 4), w5 = __shfl_sync(kFull, w, 5);
+    const double u = p + ((p01.x * w0 + p01.y * w1 + p23.x * w2) + (p23.y * w3 + p45.x * w4 + p45.y * w5));
+    const double uu = __shfl_up_sync(kFull, u, 6);
+    p = lane < 6 ? u : u + uu;                            // Phi^T: (u_pi; u_pi + u_sigma)
+  }
+  double x = 0.0;
+#pragma unroll 1
+  for (int t = 0; t < H; ++t) {
+    const double* __restrict__ pgt = sm.fac_pg[t];
+    const double bc = sm.avec[6 * t + c6];
+    const double xs = __shfl_down_sync(kFull, x, 6);
+    const double zx = lane < 6 ? x + xs : x;              // Phi x = (pi + sigma; sigma)
+    double y0 = sm.rvec[6 * t + c6], y1 = 0.0, y2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 12; k += 3) {
+      y0 = fma(pgt[6 * k + c6], __shfl_sync(kFull, zx, k), y0);
+      y1 = fma(pgt[6 * (k + 1) + c6], __shfl_sync(kFull, zx, k + 1), y1);
+      y2 = fma(pgt[6 * (k + 2) + c6], __shfl_sync(kFull, zx, k + 2), y2);
+    }
+    const double y = y0 + (y1 + y2);
+    const double q0 = __shfl_sync(kFull, y, 0), q1 = __shfl_sync(kFull, y, 1), q2 = __shfl_sync(kFull, y, 2);
+    const double q3 = __shfl_sync(kFull, y, 3), q4 = __shfl_sync(kFull, y, 4), q5 = __shfl_sync(kFull, y, 5);
+    const double* __restrict__ jr = sm.fac_j[t] + 6 * c6;
+    const double2 j01 = ldd2(jr), j23 = ldd2(jr + 2), j45 = ldd2(jr + 4);
+    const double v = (j01.x * q0 + j01.y * q1 + j23.x * q2) + (j23.y * q3 + j45.x * q4 + j45.y * q5);
+    const double v0 = __shfl_sync(kFull, v, 0), v1 = __shfl_sync(kFull, v, 1), v2 = __shfl_sync(kFull, v, 2);
+    const double v3 = __shfl_sync(kFull, v, 3), v4 = __shfl_sync(kFull, v, 4), v5 = __shfl_sync(kFull, v, 5);
+    const double* __restrict__ nb = sm.nblk[t];
+    const double d0 = nb[tri(c6, 0)];                                              // row c6 of the packed symmetric D_t
+    const double d1 = c6 >= 1 ? nb[tri(c6, 1)] : nb[tri(1, c6)];
+    const double d2 = c6 >= 2 ? nb[tri(c6, 2)] : nb[tri(2, c6)];
+    const double d3 = c6 >= 3 ? nb[tri(c6, 3)] : nb[tri(3, c6)];
+    const double d4 = c6 >= 4 ? nb[tri(c6, 4)] : nb[tri(4, c6)];
+    const double d5 = nb[tri(5, c6)];
+    const double a = bc - ((d0 * v0 + d1 * v1 + d2 * v2) + (d3 * v3 + d4 * v4 + d5 * v5));
+    const double as = __shfl_up_sync(kFull, a, 6);
+    x = lane < 6 ? zx + 0.5 * a : x + as;                 // Phi x + Gam a
+    if (lane < 6) sm.avec[6 * t + lane] = v;
   }
 }
 
@@ -714,11 +1042,16 @@ __device__ __forceinline__ void factor_psi(Smem<H>& sm, const RgMpcDev* __restri
   }
   __syncthreads();
   RG_TOC(12);
-  psi_build_rows<H>(sm, ws, t_begin);
-  __syncthreads();
-  RG_TOC(10);
-  if constexpr (Cfg<H>::CHOL_W == 4) cholesky_rows<H>(sm, 6 * t_begin);
-  else cholesky_rows_w<H, Cfg<H>::CHOL_W>(sm, 6 * t_begin);
+  if constexpr (Cfg<H>::RICCATI) {
+    if (threadIdx.x < 32) riccati_factor<H>(sm);      // the backward sweep has no reusable prefix: t_begin is not used
+    __syncthreads();
+  } else {
+    psi_build_rows<H>(sm, ws, t_begin);
+    __syncthreads();
+    RG_TOC(10);
+    if constexpr (Cfg<H>::CHOL_W == 4) cholesky_rows<H>(sm, 6 * t_begin);
+    else cholesky_rows_w<H, Cfg<H>::CHOL_W>(sm, 6 * t_begin);
+  }
   RG_TOC(11);
 }
 
@@ -742,7 +1075,10 @@ __device__ __forceinline__ void woodbury_solve(Smem<H>& sm, const Blk& b, const 
     for (int c = 0; c < 6; ++c) sm.avec[6 * b.t + c] = t6[c];
   }
   __syncthreads();
-  if (threadIdx.x < 32) tri_solve_warp0<H>(sm);
+  if (threadIdx.x < 32) {
+    if constexpr (Cfg<H>::RICCATI) riccati_solve<H>(sm);
+    else tri_solve_warp0<H>(sm);
+  }
   __syncthreads();
   if (b.act) {
     const double* v = sm.avec + 6 * b.t;
@@ -885,7 +1221,9 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
   const float in_cmd[3] = {g_cmd[3 * (size_t)env + 0], g_cmd[3 * (size_t)env + 1], g_cmd[3 * (size_t)env + 2]};
   const unsigned warm_act = (g_active && is_blk) ? (unsigned)g_active[(size_t)env * C::NB + tid] : (unsigned)RG_ACTIVE_SET_UNKNOWN;
   // stage the rank-h weights of K^-1 (host table) in the Psi buffer, which is free until the first factorisation
-  for (int i = tid; i < H * (H + 1) / 2 * H; i += blockDim.x) sm.psi[i] = ws->eig_uu[i];
+  if constexpr (!C::RICCATI) {
+    for (int i = tid; i < H * (H + 1) / 2 * H; i += blockDim.x) sm.psi[i] = ws->eig_uu[i];
+  }
   const bool stance_leg[4] = {(contact_word & 0xffu) != 0, (contact_word & 0xff00u) != 0,
                               (contact_word & 0xff0000u) != 0, (contact_word & 0xff000000u) != 0};
   const int n_stance = (int)stance_leg[0] + stance_leg[1] + stance_leg[2] + stance_leg[3];
@@ -981,6 +1319,7 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
   __syncthreads();
   RG_TOC(41);
 
+  if constexpr (!C::RICCATI) {   // the dense path needs K^-1 explicitly; the Riccati sweep works from K1, K2 alone
   // Q_t = (K1 + gamma_t K2)^-1 : 3x3 SPD angular block (packed xx,yy,zz,xz,yz,xy) + 3 scalars
   if (tid < H) {
     const double gm = ws->eig_gamma[tid];
@@ -1017,6 +1356,7 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
     if (j > k && c != d) sm.kinv_ang[tri(3 * j + c, 3 * k + d)] = v;
   }
   RG_TOC(43);
+  }
   // g~_j = 2 sum_{i>j} [ dt L_nu e_nu(i) + dt^2 (i-j-1/2) G6^T L_rho e_rho(i) ]
   // stage 1 (thread per horizon step i): the weighted errors of the free response against the reference
   // trajectory, in sm.kvec (velocity part) and sm.avec (position part) -- both are free during the setup;
@@ -1391,7 +1731,7 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
         if (active_blk && act != act_fact) tmin = (double)t_blk;
         if (!fact_valid) tmin = 0.0;
         block_reduce<C::NW>(dsum, dmx, tmin, sm.red);
-        if (tmin < (double)H) factor_psi<H>(sm, ws, blk, mproj, C::CHOL_W == 4 ? (((int)tmin) & ~1) : (int)tmin);
+        if (tmin < (double)H) factor_psi<H>(sm, ws, blk, mproj, C::RICCATI ? 0 : (C::CHOL_W == 4 ? (((int)tmin) & ~1) : (int)tmin));
         else if (tid == 0) sm.flag = 0;
         act_fact = act;
         fact_valid = true;
@@ -1718,7 +2058,8 @@ __global__ void __launch_bounds__(Cfg<H>::NT) chol_selftest_kernel(const double*
                                                                    double* __restrict__ l_out) {
   constexpr int N6 = Cfg<H>::N6;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<H>& sm = *reinterpret_cast<Smem<H>*>(smem_raw);
+  using SM = Smem<H, false>;
+  SM& sm = *reinterpret_cast<SM*>(smem_raw);
   const int tid = threadIdx.x;
   if (tid < N6) {
     for (int k = 0; k <= tid; ++k) sm.psi[prow(tid) + k] = a_dense[tid * N6 + k];
@@ -1739,11 +2080,46 @@ __global__ void __launch_bounds__(Cfg<H>::NT) chol_selftest_kernel(const double*
 
 template <int H>
 int chol_selftest_launch(const double* a, const double* b, double* x, double* l, cudaStream_t st) {
-  const size_t smem = sizeof(Smem<H>);
+  const size_t smem = sizeof(Smem<H, false>);
   cudaError_t e = cudaFuncSetAttribute(chol_selftest_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return rg_check_cuda(e, "cudaFuncSetAttribute(chol_selftest_kernel)");
   chol_selftest_kernel<H><<<1, Cfg<H>::NT, smem, st>>>(a, b, x, l);
   return rg_check_cuda(cudaGetLastError(), "chol_selftest_kernel launch");
+}
+
+// The kernel's own Riccati routines on a caller-supplied system: k1[6], k2ang[9], k2lin[3] = blocks of the stage
+// cost; d[h][21] = packed lower triangles of the D_t; b[6h] -> v[6h] with (K^-1 + blkdiag D_t) v = b.
+template <int H>
+__global__ void __launch_bounds__(32) riccati_selftest_kernel(const double* __restrict__ k1, const double* __restrict__ k2ang,
+                                                              const double* __restrict__ k2lin, const double* __restrict__ d,
+                                                              const double* __restrict__ b, double* __restrict__ v_out,
+                                                              int* __restrict__ flag_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using SM = Smem<H, true>;
+  SM& sm = *reinterpret_cast<SM*>(smem_raw);
+  const int tid = threadIdx.x;
+  if (tid < 6) sm.k1[tid] = k1[tid];
+  if (tid < 9) sm.k2ang[tid] = k2ang[tid];
+  if (tid < 3) sm.k2lin[tid] = k2lin[tid];
+  for (int i = tid; i < 21 * H; i += blockDim.x) sm.nblk[i / 21][i % 21] = d[i];
+  for (int i = tid; i < 6 * H; i += blockDim.x) sm.avec[i] = b[i];
+  __syncwarp();
+  riccati_factor<H>(sm);
+  __syncwarp();
+  riccati_solve<H>(sm);
+  __syncwarp();
+  for (int i = tid; i < 6 * H; i += blockDim.x) v_out[i] = sm.avec[i];
+  if (tid == 0) *flag_out = sm.flag;
+}
+
+template <int H>
+int riccati_selftest_launch(const double* k1, const double* k2ang, const double* k2lin, const double* d, const double* b,
+                            double* v, int* flag, cudaStream_t st) {
+  const size_t smem = sizeof(Smem<H, true>);
+  cudaError_t e = cudaFuncSetAttribute(riccati_selftest_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return rg_check_cuda(e, "cudaFuncSetAttribute(riccati_selftest_kernel)");
+  riccati_selftest_kernel<H><<<1, 32, smem, st>>>(k1, k2ang, k2lin, d, b, v, flag);
+  return rg_check_cuda(cudaGetLastError(), "riccati_selftest_kernel launch");
 }
 
 }  // namespace
@@ -1753,6 +2129,16 @@ extern "C" int rg_debug_chol_solve(int horizon, const double* a_dense, const dou
     case 5: return chol_selftest_launch<5>(a_dense, rhs, x_out, l_out, (cudaStream_t)stream);
     case 10: return chol_selftest_launch<10>(a_dense, rhs, x_out, l_out, (cudaStream_t)stream);
     case 20: return chol_selftest_launch<20>(a_dense, rhs, x_out, l_out, (cudaStream_t)stream);
+    default: rg_set_error("unsupported horizon %d", horizon); return RG_ERR_UNSUPPORTED;
+  }
+}
+
+extern "C" int rg_debug_riccati_solve(int horizon, const double* k1, const double* k2ang, const double* k2lin, const double* d,
+                                      const double* b, double* v_out, int* flag_out, void* stream) {
+  switch (horizon) {
+    case 5: return riccati_selftest_launch<5>(k1, k2ang, k2lin, d, b, v_out, flag_out, (cudaStream_t)stream);
+    case 10: return riccati_selftest_launch<10>(k1, k2ang, k2lin, d, b, v_out, flag_out, (cudaStream_t)stream);
+    case 20: return riccati_selftest_launch<20>(k1, k2ang, k2lin, d, b, v_out, flag_out, (cudaStream_t)stream);
     default: rg_set_error("unsupported horizon %d", horizon); return RG_ERR_UNSUPPORTED;
   }
 }

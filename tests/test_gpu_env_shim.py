@@ -39,6 +39,8 @@ def test_env_shim_4096_envs_100_steps_equals_the_unshimmed_controller(rg_lib, cu
     assert obs.shape == (n, 37) and obs.is_cuda
     gen = torch.Generator(device="cpu").manual_seed(3)
     n_resets = 0
+    saw_swing = torch.zeros((), dtype=torch.bool, device=cuda_device)
+    max_joint_travel = torch.zeros((), dtype=torch.float32, device=cuda_device)
     for k in range(steps):
         act = torch.stack([torch.rand(n, generator=gen) * 0.35, (torch.rand(n, generator=gen) - 0.5) * 0.8], dim=1).to(cuda_device)
         shadow.update_controller_params(act)
@@ -60,10 +62,11 @@ def test_env_shim_4096_envs_100_steps_equals_the_unshimmed_controller(rg_lib, cu
             assert torch.all(sim.GetTimeSinceReset()[fell] == 0) and torch.all(env.episode_steps[fell] == 0)
             shadow.reset(fell)
         assert int(sim.controller.unverified_count()) == 0
+        saw_swing |= (sim.robot.GetFootContacts()[alive] == 0).any()
+        max_joint_travel = torch.maximum(max_joint_travel, (sim.physics.joint_angles - sim.physics._q0).abs().max())
     assert n_resets >= 4
-    # the swing legs really moved: contacts switched during the rollout and the joints left the start pose
-    assert (sim.robot.GetFootContacts() == 0).any()
-    assert (sim.physics.joint_angles - sim.physics._q0).abs().max() > 0.05
+    # the loop is closed: swing legs lifted (contacts switched off on envs that did not fall) and joints left the start pose
+    assert bool(saw_swing) and float(max_joint_travel) > 0.05
 
 
 @pytest.mark.parametrize("fuse", [True, False])
