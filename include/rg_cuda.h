@@ -333,6 +333,16 @@ typedef struct rg_controller_state {
 int rg_control_step(const void* mpc_workspace, const void* robot_workspace, int n_env,
                     const rg_controller_state* s_host, void* stream);
 
+/* The same control step as ONE CUDA-graph launch (small batches are launch-bound: prologue + solve + epilogue are three
+ * dependent kernels of a few microseconds each).  rg_control_step_graph_create captures rg_control_step with the pointers
+ * of `s` baked in and -- to configure kernels and surface argument errors outside the capture -- EXECUTES ONE STEP while
+ * doing so (on `stream`): call it in place of a control step, not before one; it synchronises `stream`.  rg_control_step_graph_launch replays the
+ * step on `stream` without synchronising.  Re-create the graph when any buffer of `s` moves or n_env changes. */
+int rg_control_step_graph_create(const void* mpc_workspace, const void* robot_workspace, int n_env,
+                                 const rg_controller_state* s_host, void* stream, void** graph_out);
+int rg_control_step_graph_launch(void* graph, void* stream);
+int rg_control_step_graph_destroy(void* graph);
+
 /* ---- "next" row: batched HYBRID motor model ----------------------------
  * Replaces RobotMotorModel.convert_to_torque HYBRID branch (simple_motor.py:128-139):
  * tau = -kp (q - q_des) - kd (qd - qd_des) + tau_ff ; no clipping (robot.py:40-45). */

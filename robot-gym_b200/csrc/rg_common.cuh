@@ -91,6 +91,7 @@ struct RgRobotDev {
 void rg_set_error(const char* fmt, ...);
 int rg_check_cuda(cudaError_t e, const char* what);
 void rg_count_launch();
+extern "C" uint64_t rg_launch_count(void);
 
 // launchers implemented in the .cu files
 struct rg_controller_state;

@@ -134,6 +134,7 @@ struct Smem {
   double nblk[H][21];              // per time step: lower triangle of sum_legs B E^-1 B^T (setup: (K1 + gamma_t K2)^-1 scratch)
   double red[3][8];
   int flag;
+  int solver_warp;                 // the warp that runs the single-warp phases (sweeps): see solve_env
 };
 
 __device__ __forceinline__ int tri(int i, int k) { return i * (i + 1) / 2 + k; }
@@ -476,7 +477,7 @@ __device__ RG_HEAVY_INLINE void tri_solve_warp0(SM& sm) {
   constexpr int RPL = Cfg<H>::RPL;
   constexpr int NL = N6 / RPL;
   static_assert(NL * RPL == N6 && NL <= 32, "rows must split evenly over the lanes of one warp");
-  const int lane = threadIdx.x;   // caller guarantees threadIdx.x < 32
+  const int lane = threadIdx.x & 31;   // one warp runs this routine (sm.solver_warp)
   const bool active = lane < NL;
   const int i0 = active ? lane * RPL : 0;
   double x[RPL], rd[RPL], lb[RPL][RPL], l[RPL][RPL];
@@ -647,7 +648,7 @@ __device__ __forceinline__ double pick_sym3(const double* m, int r, int c) {
 
 template <int H, class SM>
 __device__ RG_HEAVY_INLINE void riccati_factor(SM& sm) {
-  const int lane = threadIdx.x;   // caller guarantees threadIdx.x < 32
+  const int lane = threadIdx.x & 31;   // one warp runs this routine (sm.solver_warp)
   const int r6 = lane < 18 ? lane / 3 : 0, cp = lane < 18 ? lane - 3 * (lane / 3) : 0;      // 6 x 6 products: 18 lanes x 2 outputs
   const int k12 = lane < 24 ? lane >> 1 : 0, ch = lane & 1;                                  // 12 x 6 products: 24 lanes x 3 outputs
   // the (k, l), l <= k, entries of the 12 x 12 lower triangle this lane updates in step 8 (78 entries, <= 3 per lane)
@@ -833,7 +834,7 @@ __device__ RG_HEAVY_INLINE void riccati_factor(SM& sm) {
 // lanes 0..5; everything moves by warp shuffles: no barrier and no shared-memory round trip on the chain.
 template <int H, class SM>
 __device__ RG_HEAVY_INLINE void riccati_solve(SM& sm) {
-  const int lane = threadIdx.x;   // caller guarantees threadIdx.x < 32
+  const int lane = threadIdx.x & 31;   // one warp runs this routine (sm.solver_warp)
   const int k12 = lane < 12 ? lane : 0, c6 = lane < 6 ? lane : 0;
   double p = 0.0;
 #pragma unroll 1
@@ -1043,7 +1044,7 @@ __device__ __forceinline__ void factor_psi(Smem<H>& sm, const RgMpcDev* __restri
   __syncthreads();
   RG_TOC(12);
   if constexpr (Cfg<H>::RICCATI) {
-    if (threadIdx.x < 32) riccati_factor<H>(sm);      // the backward sweep has no reusable prefix: t_begin is not used
+    if ((int)(threadIdx.x >> 5) == sm.solver_warp) riccati_factor<H>(sm);      // the backward sweep has no reusable prefix: t_begin is not used
     __syncthreads();
   } else {
     psi_build_rows<H>(sm, ws, t_begin);
@@ -1075,7 +1076,7 @@ __device__ __forceinline__ void woodbury_solve(Smem<H>& sm, const Blk& b, const 
     for (int c = 0; c < 6; ++c) sm.avec[6 * b.t + c] = t6[c];
   }
   __syncthreads();
-  if (threadIdx.x < 32) {
+  if ((int)(threadIdx.x >> 5) == sm.solver_warp) {
     if constexpr (Cfg<H>::RICCATI) riccati_solve<H>(sm);
     else tri_solve_warp0<H>(sm);
   }
@@ -1246,7 +1247,20 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
   sincos(yaw, &sy, &cy);
 
   // ---------------------------------------------------------------- setup (thread 0..; tiny)
-  if (tid == 0) sm.flag = 0;
+  if (tid == 0) {
+    sm.flag = 0;
+    // The triangular / Riccati sweeps are executed by ONE warp of the CTA.  Warp slots map onto the four SM
+    // sub-partitions by (slot mod 4), and the first warp of every CTA lands on the same one or two of them: with
+    // "warp 0 sweeps" all resident envs would queue their serial phases on one scheduler.  Rotate the choice with
+    // the CTA's position among the SM's warp slots so that the sweeps of co-resident envs spread over all four.
+    unsigned slot;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(slot));
+    const unsigned group = slot / C::NW;
+    sm.solver_warp = C::NW >= 4 ? (int)(group % C::NW) : (C::NW == 2 ? (int)((group >> 1) & 1u) : 0);
+#ifdef RG_SOLVER_WARP0
+    sm.solver_warp = 0;
+#endif
+  }
 
   RG_TOC(40);
   // T(rpy): angular velocity -> rpy rate;  K2_ang = 2 dt^4 T^T diag(w_rpy) T
@@ -2018,12 +2032,30 @@ int configure_kernel(const void* kernel, size_t smem, int min_blocks, const char
   return RG_OK;
 }
 
+// SM count of the current device (cached per device: this sits on the launch path)
+int sm_count() {
+  static std::mutex mutex;
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  std::lock_guard<std::mutex> lock(mutex);
+  if (cached[dev] == 0) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = sms > 0 ? sms : 148;
+  }
+  return cached[dev];
+}
+
 template <int H>
 int launch_h(const RgMpcDev* ws, int n_env, const rg_mpc_io& io, int two_kernel, cudaStream_t stream) {
   const size_t smem = sizeof(Smem<H>);
   RgMpcScratch* scratch = (RgMpcScratch*)((char*)ws + RG_MPC_SCRATCH_OFFSET);
   int rc;
-  if (two_kernel) {
+  const int slots = sm_count() * Cfg<H>::MIN_BLOCKS;     // CTAs resident at once
+  // A batch that fits one wave gains nothing from the split (every env has an SM slot of its own from the start):
+  // one launch of the complete kernel instead of two -- this is the small-N latency path.
+  if (two_kernel && n_env > slots) {
     // lean active-set kernel on every env, then the complete solver on whatever it queued
     rc = configure_kernel((const void*)mpc_solve_kernel<H, true>, smem, Cfg<H>::MIN_BLOCKS, "cudaFuncSetAttribute(mpc_solve_kernel lean)");
     if (rc != RG_OK) return rc;
@@ -2033,11 +2065,7 @@ int launch_h(const RgMpcDev* ws, int n_env, const rg_mpc_io& io, int two_kernel,
     rg_count_launch();
     rc = rg_check_cuda(cudaGetLastError(), "mpc_solve_kernel (lean) launch");
     if (rc != RG_OK) return rc;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int slots = sms * Cfg<H>::MIN_BLOCKS;          // as many CTAs as fit at once: an empty queue costs one wave of exits
-    const int grid = n_env < slots ? n_env : slots;
+    const int grid = n_env < slots ? n_env : slots;       // as many CTAs as fit at once: an empty queue costs one wave of exits
     mpc_fallback_kernel<H><<<grid, Cfg<H>::NT, smem, stream>>>(ws, scratch, n_env, io);
     rg_count_launch();
     return rg_check_cuda(cudaGetLastError(), "mpc_fallback_kernel launch");
@@ -2103,6 +2131,7 @@ __global__ void __launch_bounds__(32) riccati_selftest_kernel(const double* __re
   if (tid < 3) sm.k2lin[tid] = k2lin[tid];
   for (int i = tid; i < 21 * H; i += blockDim.x) sm.nblk[i / 21][i % 21] = d[i];
   for (int i = tid; i < 6 * H; i += blockDim.x) sm.avec[i] = b[i];
+  if (tid == 0) sm.solver_warp = 0;
   __syncwarp();
   riccati_factor<H>(sm);
   __syncwarp();

@@ -760,3 +760,65 @@ extern "C" int rg_control_step(const void* mpc_ws, const void* robot_ws, int n_e
   rg_count_launch();
   return rg_check_cuda(cudaGetLastError(), "step_epilogue_kernel launch");
 }
+
+// ---- the control step as ONE graph launch ---------------------------------------------------------------------------
+// For small batches the step is launch-bound: prologue, solve (one kernel when the batch fits a wave) and epilogue are
+// three dependent launches of a few microseconds each.  Captured once into a CUDA graph they are replayed with a single
+// cudaGraphLaunch.  The graph bakes in the pointers of `s`: the caller re-creates it when a buffer moves.
+struct RgStepGraph {
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+  int kernels;
+};
+
+extern "C" int rg_control_step_graph_create(const void* mpc_ws, const void* robot_ws, int n_env, const rg_controller_state* s,
+                                            void* stream, void** graph_out) {
+  RG_REQUIRE(mpc_ws && robot_ws && s && graph_out && n_env > 0, "rg_control_step_graph_create");
+  *graph_out = nullptr;
+  // one eager step on the caller's stream first: kernel attributes get configured outside the capture, and argument
+  // errors surface here with their own message.  The controller state advances by this step -- the caller accounts for it
+  // by creating the graph INSTEAD of a step, not before one (see rg_cuda.h).
+  int rc = rg_control_step(mpc_ws, robot_ws, n_env, s, stream);
+  if (rc == RG_OK) rc = rg_check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "graph warm-up step");
+  if (rc != RG_OK) return rc;
+  cudaStream_t cap = nullptr;
+  rc = rg_check_cuda(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking), "graph capture stream");
+  if (rc != RG_OK) return rc;
+  const uint64_t before = rg_launch_count();
+  RgStepGraph* g = new RgStepGraph{nullptr, nullptr, 0};
+  cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+  if (e == cudaSuccess) {
+    rc = rg_control_step(mpc_ws, robot_ws, n_env, s, cap);
+    e = cudaStreamEndCapture(cap, &g->graph);
+    if (rc != RG_OK) e = cudaErrorUnknown;
+  }
+  if (e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+  cudaStreamDestroy(cap);
+  if (e != cudaSuccess) {
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+    cudaGetLastError();
+    if (rc == RG_OK) rc = rg_check_cuda(e, "control-step graph capture");
+    return rc;
+  }
+  g->kernels = (int)(rg_launch_count() - before);
+  *graph_out = g;
+  return RG_OK;
+}
+
+extern "C" int rg_control_step_graph_launch(void* graph, void* stream) {
+  RG_REQUIRE(graph, "rg_control_step_graph_launch");
+  RgStepGraph* g = (RgStepGraph*)graph;
+  const int rc = rg_check_cuda(cudaGraphLaunch(g->exec, (cudaStream_t)stream), "cudaGraphLaunch(control step)");
+  for (int i = 0; i < g->kernels; ++i) rg_count_launch();
+  return rc;
+}
+
+extern "C" int rg_control_step_graph_destroy(void* graph) {
+  if (!graph) return RG_OK;
+  RgStepGraph* g = (RgStepGraph*)graph;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+  return RG_OK;
+}

@@ -62,8 +62,10 @@ class BatchedMPCController(Controller):
 
     MOTOR_CONTROL_MODE = MOTOR_CONTROL_HYBRID      # mpc_controller.py:16
 
+    GRAPH_MAX_ENVS = 2048          # below this a control step is launch-bound: replay it as one CUDA graph
+
     def __init__(self, robot, get_time_since_reset, horizon=10, mpc_overrides=None, squeeze_single=True,
-                 warm_start=True):
+                 warm_start=True, use_graph=None):
         """``robot``: batched state provider with the getter names of robot.py (see
         ``SyntheticRobotBatch``); ``get_time_since_reset``: callable returning a float or an
         ``[N]`` float64 tensor (Simulation.GetTimeSinceReset, core/simulation.py:141-142).
@@ -85,6 +87,10 @@ class BatchedMPCController(Controller):
         self.horizon = int(horizon)
         self._squeeze_single = bool(squeeze_single)
         n, dev = self.num_envs, self.device
+        # one graph launch per step instead of three kernel launches (rg_control_step_graph_*): default for small batches
+        self._use_graph = (n <= self.GRAPH_MAX_ENVS) if use_graph is None else bool(use_graph)
+        self._graph = None
+        self._graph_invalidations = 0
 
         # --- C-ABI workspaces (the analogue of _setup_controller, mpc_controller.py:28-66)
         c = self._constants
@@ -260,8 +266,9 @@ class BatchedMPCController(Controller):
     def _refresh_inputs(self):
         """Pull the robot getters (robot.py:79-236,389-397).  A tensor whose storage, shape and dtype are the ones
         validated last step is not validated again; anything new is checked for dtype, contiguity, [N, ...]
-        shape, device and alignment before its pointer reaches a kernel."""
+        shape, device and alignment before its pointer reaches a kernel.  Returns True if any pointer changed."""
         n, cache, st = self.num_envs, self._input_cache, self._state
+        changed = False
         for field, getter, dtype, tail, align in self._ROBOT_INPUTS:
             t = getattr(self._robot, getter)()
             if field == "foot_positions_base" and isinstance(t, torch.Tensor) and t.dim() == 3:
@@ -270,7 +277,9 @@ class BatchedMPCController(Controller):
             if key is None or cache.get(field) != key:
                 setattr(st, field, rg._ptr(t, dtype, tail, n=n, device=self.device, align=align))
                 cache[field] = (t.data_ptr(), t.shape, t.dtype)
+                changed = True
             cache[field + "_ref"] = t          # keep the storage alive until the kernels have consumed it
+        return changed
 
     def attach_torque_consumer(self, motor_velocities_getter, strength_ratios=None, applied_motor_torques=None):
         """Fuse the HYBRID motor model of the first physics tick into the step's epilogue:
@@ -283,6 +292,7 @@ class BatchedMPCController(Controller):
         self.applied_motor_torques = applied_motor_torques
         self._motor_velocities_getter = motor_velocities_getter
         self._strength_ratios = strength_ratios
+        self._destroy_graph()                                  # the captured step does not write the torques yet
         self._state.applied_motor_torques = rg._ptr(applied_motor_torques, f32, (12,), n=n, device=dev)
         self._state.motor_strength_ratios = rg._ptr(strength_ratios, f32, (12,), allow_none=True, n=n, device=dev)
         return applied_motor_torques
@@ -291,18 +301,52 @@ class BatchedMPCController(Controller):
         if self._adapter is not None:
             self._adapter.refresh()
         torch.sub(self._clock(), self.reset_time, out=self.time_since_reset)
-        self._refresh_inputs()
+        changed = self._refresh_inputs()
         if getattr(self, "_motor_velocities_getter", None) is not None:
             qd = self._motor_velocities_getter()
             key = (qd.data_ptr(), qd.shape, qd.dtype)
             if self._input_cache.get("motor_velocities") != key:
                 self._state.motor_velocities = rg._ptr(qd, torch.float32, (12,), n=self.num_envs, device=self.device)
                 self._input_cache["motor_velocities"] = key
+                changed = True
             self._input_cache["motor_velocities_ref"] = qd
+        lib = rg.load()
         with torch.cuda.device(self.device):
-            rg.check(rg.load().rg_control_step(self._mpc_ws.ptr, self._robot_ws.ptr, self.num_envs,
-                                               ctypes.byref(self._state), rg.current_stream_ptr()))
+            if not self._use_graph:
+                rg.check(lib.rg_control_step(self._mpc_ws.ptr, self._robot_ws.ptr, self.num_envs,
+                                             ctypes.byref(self._state), rg.current_stream_ptr()))
+            else:
+                if changed and self._graph is not None:          # a buffer moved: the captured pointers are stale
+                    self._destroy_graph()
+                    self._graph_invalidations += 1
+                    if self._graph_invalidations >= 3:            # a provider that hands out fresh tensors every step
+                        self._use_graph = False
+                        rg.check(lib.rg_control_step(self._mpc_ws.ptr, self._robot_ws.ptr, self.num_envs,
+                                                     ctypes.byref(self._state), rg.current_stream_ptr()))
+                        return self.action
+                if self._graph is None:
+                    # creating the graph executes this step eagerly (and synchronises once)
+                    handle = ctypes.c_void_p()
+                    rg.check(lib.rg_control_step_graph_create(self._mpc_ws.ptr, self._robot_ws.ptr, self.num_envs,
+                                                              ctypes.byref(self._state), rg.current_stream_ptr(),
+                                                              ctypes.byref(handle)))
+                    self._graph = handle
+                else:
+                    rg.check(lib.rg_control_step_graph_launch(self._graph, rg.current_stream_ptr()))
         return self.action
+
+    def _destroy_graph(self):
+        if self._graph is not None:
+            try:
+                rg.load().rg_control_step_graph_destroy(self._graph)
+            finally:
+                self._graph = None
+
+    def __del__(self):
+        try:
+            self._destroy_graph()
+        except Exception:
+            pass
 
     def unverified_count(self):
         """Number of envs (device scalar, no synchronisation) whose last stance QP did NOT end in a verified KKT

@@ -42,14 +42,16 @@ class BatchedPhysics:
 
 
 class SyntheticPhysics(BatchedPhysics):
-    """NOT a physics engine: a deterministic stand-in for tests and demos.  Every joint is a damped unit of inertia
-    on a soft spring towards the start pose (so that feed-forward stance torques cannot run away), the base is held
-    level with a small commanded drift, and a foot is 'in contact' while its base-frame height is within
-    ``contact_band`` of the standing height.  It closes the loop just enough to exercise the whole control path:
-    swing legs lift (contacts switch off), PD torques pull joints to their IK targets, resets re-arm envs."""
+    """NOT a physics engine: a deterministic stand-in for tests and demos.  Every joint is a damped inertia driven by
+    the applied motor torque (plus a weak spring towards the start pose against drift); the ground is a one-sided
+    constraint on each foot -- a tick that would push a foot below its standing height is undone for that leg
+    (joints locked), which is what the feed-forward stance torques do all the time; the base is held level.  A foot
+    is 'in contact' while its base-frame height is within ``contact_band`` of the standing height.  It closes the
+    loop just enough to exercise the whole control path: swing legs lift (contacts switch off), PD torques pull the
+    joints to their IK targets, stance legs stay planted, resets re-arm envs."""
 
-    def __init__(self, description, num_envs, kinematics, device="cuda", inertia=0.05, damping=2.0, stiffness=20.0,
-                 contact_band=0.03):
+    def __init__(self, description, num_envs, kinematics, device="cuda", inertia=0.02, damping=0.5, stiffness=5.0,
+                 contact_band=0.004):
         self.description, self.num_envs, self.device = description, int(num_envs), torch.device(device)
         self._kin = kinematics
         mc, c = description.GetMotorConstants(), description.GetConstants()
@@ -67,11 +69,11 @@ class SyntheticPhysics(BatchedPhysics):
         self.forced_airborne = torch.zeros(n, dtype=torch.bool, device=dev)     # tests: envs that have "fallen"
         self._inertia, self._damping, self._stiffness, self._band = inertia, damping, stiffness, contact_band
         self.reset()
-        feet = self._kin.ComputeFootPositionsInBaseFrame(self.motor_angles()).view(n, 4, 3)
-        self._stand_z = feet[:, :, 2].min().item()
+        feet = self._kin.ComputeFootPositionsInBaseFrame(self._motor_angles(self.joint_angles)).view(n, 4, 3)
+        self._stand_z = feet[0, :, 2].clone()                                    # per leg (ghost is left/right asymmetric)
 
-    def motor_angles(self):
-        return ((self.joint_angles - self._offset) * self._direction).contiguous()
+    def _motor_angles(self, joint_angles):
+        return ((joint_angles - self._offset) * self._direction).contiguous()
 
     def reset(self, env_ids=None):
         sel = slice(None) if env_ids is None else env_ids
@@ -84,13 +86,16 @@ class SyntheticPhysics(BatchedPhysics):
         self.forced_airborne[sel] = False
 
     def step(self, applied_motor_torques, dt):
+        n = self.num_envs
         acc = (applied_motor_torques - self._damping * self.joint_velocities -
                self._stiffness * (self.joint_angles - self._q0)) / self._inertia
-        self.joint_velocities += dt * acc                       # semi-implicit Euler
-        self.joint_angles += dt * self.joint_velocities
-        feet = self._kin.ComputeFootPositionsInBaseFrame(self.motor_angles()).view(self.num_envs, 4, 3)
-        contact = feet[:, :, 2] <= self._stand_z + self._band
-        contact &= ~self.forced_airborne[:, None]
+        qd = self.joint_velocities + dt * acc                     # semi-implicit Euler, tentatively
+        q = self.joint_angles + dt * qd
+        z = self._kin.ComputeFootPositionsInBaseFrame(self._motor_angles(q)).view(n, 4, 3)[:, :, 2]
+        blocked = (z < self._stand_z).repeat_interleave(3, dim=1)  # the ground: this leg's tick is undone
+        self.joint_angles.copy_(torch.where(blocked, self.joint_angles, q))
+        self.joint_velocities.copy_(torch.where(blocked, torch.zeros_like(qd), qd))
+        contact = (z <= self._stand_z + self._band) & ~self.forced_airborne[:, None]
         self.foot_contacts.copy_(contact.to(torch.uint8))
 
 

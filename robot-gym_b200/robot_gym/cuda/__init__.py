@@ -30,7 +30,8 @@ EXPORTED_SYMBOLS = (
     "rg_mpc_build_solve_warm", "rg_mpc_build_solve_io",
     "rg_robot_calibrate_ik", "rg_robot_workspace_bytes", "rg_robot_setup",
     "rg_gait_step", "rg_com_velocity_update", "rg_swing_targets", "rg_leg_ik", "rg_leg_fk", "rg_state_from_sim",
-    "rg_force_to_torque", "rg_pack_hybrid_action", "rg_control_step", "rg_hybrid_motor_torque", "rg_hybrid_motor_torque_ex",
+    "rg_force_to_torque", "rg_pack_hybrid_action", "rg_control_step", "rg_control_step_graph_create", "rg_control_step_graph_launch", "rg_control_step_graph_destroy",
+    "rg_hybrid_motor_torque", "rg_hybrid_motor_torque_ex",
     "rg_measure_fma_peak", "rg_launch_count", "rg_last_error", "rg_version",
 )
 
@@ -140,6 +141,9 @@ def load(build_if_missing: bool = False):
     lib.rg_force_to_torque.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.rg_pack_hybrid_action.argtypes = [c_void_p, c_int] + [c_void_p] * 5 + [c_void_p]
     lib.rg_control_step.argtypes = [c_void_p, c_void_p, c_int, POINTER(ControllerState), c_void_p]
+    lib.rg_control_step_graph_create.argtypes = [c_void_p, c_void_p, c_int, POINTER(ControllerState), c_void_p, POINTER(c_void_p)]
+    lib.rg_control_step_graph_launch.argtypes = [c_void_p, c_void_p]
+    lib.rg_control_step_graph_destroy.argtypes = [c_void_p]
     lib.rg_hybrid_motor_torque.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.rg_hybrid_motor_torque_ex.argtypes = [c_void_p, c_int] + [c_void_p] * 6 + [c_void_p]
     lib.rg_measure_fma_peak.argtypes = [c_int, c_int, POINTER(c_double)]

@@ -22,20 +22,20 @@ class SyntheticRobotBatch:
         self.num_motors = 12
         self.load(states)
 
+    _FIELDS = ("time_since_reset", "foot_contacts", "base_velocity_world", "base_orientation_xyzw", "base_rpy",
+               "base_rpy_rate", "foot_positions_base", "motor_angles")
+
     def load(self, states: SyntheticStates, non_blocking=False):
-        """Host -> device copy of a full state batch (pinned staging makes it asynchronous)."""
+        """Host -> device copy of a full state batch (pinned staging makes it asynchronous).  Existing device tensors
+        are overwritten IN PLACE, so the storage the controller (and a captured CUDA graph) points at stays put."""
         dev = self.device
-        def up(a):
-            t = torch.from_numpy(a)
-            return t.to(dev, non_blocking=non_blocking)
-        self.time_since_reset = up(states.time_since_reset)
-        self.foot_contacts = up(states.foot_contacts)
-        self.base_velocity_world = up(states.base_velocity_world)
-        self.base_orientation_xyzw = up(states.base_orientation_xyzw)
-        self.base_rpy = up(states.base_rpy)
-        self.base_rpy_rate = up(states.base_rpy_rate)
-        self.foot_positions_base = up(states.foot_positions_base)
-        self.motor_angles = up(states.motor_angles)
+        for name in self._FIELDS:
+            src = torch.from_numpy(getattr(states, name))
+            cur = getattr(self, name, None)
+            if isinstance(cur, torch.Tensor) and cur.shape == src.shape and cur.dtype == src.dtype and cur.device.type == dev.type:
+                cur.copy_(src, non_blocking=non_blocking)
+            else:
+                setattr(self, name, src.to(dev, non_blocking=non_blocking))
 
     # ---- description passthrough (ghost/ghost.py:7-30)
     def GetCtrlConstants(self):

@@ -131,7 +131,7 @@ def test_single_env_adapter_for_a_stock_robot(rg_lib, cuda_device):
     clock = {"t": float(seq[0].time_since_reset[0])}
     ctl = BatchedMPCController(stub, lambda: clock["t"])
     ref_robot = SyntheticRobotBatch(GHOST, seq[0], device=cuda_device)
-    ref = BatchedMPCController(ref_robot, ref_robot.GetTimeSinceReset, squeeze_single=False)
+    ref = BatchedMPCController(ref_robot, ref_robot.GetTimeSinceReset, squeeze_single=False, use_graph=False)   # eager launches
     assert ctl.num_envs == 1 and ctl._adapter is not None
     for k in range(12):
         stub._st = seq[k]
@@ -146,3 +146,34 @@ def test_single_env_adapter_for_a_stock_robot(rg_lib, cuda_device):
         np.testing.assert_array_equal(a, b.cpu().numpy()[0])
     ctl.reset()
     assert float(ctl.reset_time[0]) == clock["t"]
+
+
+@pytest.mark.parametrize("n", [1, 700])
+def test_graph_replay_of_the_control_step_equals_eager_launches(rg_lib, cuda_device, n):
+    """Small batches replay the step as ONE CUDA graph (rg_control_step_graph_*): same commands, bit for bit, as the
+    three eager launches, over a rollout whose state is updated in place; a provider that hands out fresh tensors
+    every step makes the controller fall back to eager launches instead of re-capturing for ever."""
+    seq = synthetic.make_state_sequence(n, 16, GHOST, seed=123)
+    robots = [SyntheticRobotBatch(GHOST, seq[0], device=cuda_device) for _ in range(2)]
+    ctl_g = BatchedMPCController(robots[0], robots[0].GetTimeSinceReset, squeeze_single=False, use_graph=True)
+    ctl_e = BatchedMPCController(robots[1], robots[1].GetTimeSinceReset, squeeze_single=False, use_graph=False)
+    launches = []
+    for k in range(16):
+        for r in robots:
+            r.load(seq[k])                                   # in place: pointers stay put
+        for c in (ctl_g, ctl_e):
+            c.update_controller_params((0.25, 0.0, -0.1))
+        before = rg.launch_count()
+        a_g = ctl_g.get_action().clone()
+        launches.append(rg.launch_count() - before)
+        a_e = ctl_e.get_action().clone()
+        torch.cuda.synchronize()
+        assert torch.equal(a_g, a_e), k
+        assert torch.equal(ctl_g.solve_info, ctl_e.solve_info)
+    assert ctl_g._graph is not None and ctl_g._use_graph
+    assert launches[0] >= 6 and all(l == 3 for l in launches[1:])          # create = eager step + capture; replay = 3 kernels
+    # fresh tensors every step -> stale pointers -> after a few re-captures the controller goes eager
+    for k in range(6):
+        robots[0].base_rpy = robots[0].base_rpy.clone()
+        ctl_g.get_action()
+    assert not ctl_g._use_graph and ctl_g._graph is None
