@@ -649,8 +649,13 @@ __device__ __forceinline__ double pick_sym3(const double* m, int r, int c) {
 template <int H, class SM>
 __device__ RG_HEAVY_INLINE void riccati_factor(SM& sm) {
   const int lane = threadIdx.x & 31;   // one warp runs this routine (sm.solver_warp)
-  const int r6 = lane < 18 ? lane / 3 : 0, cp = lane < 18 ? lane - 3 * (lane / 3) : 0;      // 6 x 6 products: 18 lanes x 2 outputs
-  const int k12 = lane < 24 ? lane >> 1 : 0, ch = lane & 1;                                  // 12 x 6 products: 24 lanes x 3 outputs
+  // Lane roles (indices of lanes without the role are clamped to 0: every lane computes, only role lanes store --
+  // predicated stores instead of divergent branches around each step)
+  const bool l18 = lane < 18, l24 = lane < 24, l9 = lane < 9, l22 = lane >= 9 && lane < 18;
+  const int r6 = l18 ? lane / 3 : 0, cp = l18 ? lane - 3 * (lane / 3) : 0;     // 6 x 6 products: row r6, columns 2 cp, 2 cp + 1
+  const int k12 = l24 ? lane >> 1 : 0, ch = lane & 1;                           // 12 x 6 products: row k12, columns 3 ch ..
+  const int gr = l9 ? lane / 3 : 0, gc = l9 ? lane - 3 * (lane / 3) : 0;        // 3 x 3 blocks 11 / 21 of Y^-1
+  const int r22 = l22 ? (lane - 9) / 3 : 0, c22 = l22 ? (lane - 9) - 3 * ((lane - 9) / 3) : 0;   // block 22
   // the (k, l), l <= k, entries of the 12 x 12 lower triangle this lane updates in step 8 (78 entries, <= 3 per lane)
   int pk[3], pl[3];
 #pragma unroll
@@ -658,169 +663,165 @@ __device__ RG_HEAVY_INLINE void riccati_factor(SM& sm) {
     const int e = lane + 32 * i;
     int k = 0;
     while ((k + 1) * (k + 2) / 2 <= e) ++k;
-    pk[i] = e < 78 ? k : -1;
-    pl[i] = e - k * (k + 1) / 2;
+    pk[i] = e < 78 ? k : 0;
+    pl[i] = e < 78 ? e - k * (k + 1) / 2 : 0;
   }
-  for (int e = lane; e < 144; e += 32) {
-    const int r = e / 12, c = e - 12 * r;
-    double v = 0.0;
-    if (r < 3 && c < 3) v = sm.k2ang[3 * r + c];
-    else if (r == c) v = r < 6 ? sm.k2lin[r - 3] : sm.k1[r - 6];
-    sm.pm[e] = v;
+  // stage cost Q = blkdiag(K2, K1) at this lane's two (r6, c) pairs
+  double qa[2], qc[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int c = 2 * cp + j;
+    qa[j] = (r6 < 3 && c < 3) ? sm.k2ang[3 * r6 + c] : ((r6 == c && r6 >= 3) ? sm.k2lin[r6 - 3] : 0.0);
+    qc[j] = r6 == c ? sm.k1[r6] : 0.0;
   }
+  double* __restrict__ md = sm.m6[RM_D];
+  double* __restrict__ ms = sm.m6[RM_S];
+  double* __restrict__ mu = sm.m6[RM_U];
+  double* __restrict__ my = sm.m6[RM_Y];
+  double* __restrict__ myi = sm.m6[RM_YI];
+  double* __restrict__ mg = sm.m6[RM_G];
+  // P_h = Q, and from it the inputs of the first stage (t = H - 1):  PG = P Gam,  S = Gam^T P Gam,  D_t unpacked
+  for (int e = lane; e < 144; e += 32) sm.pm[e] = 0.0;
   if (lane == 0) sm.flag = 0;
+  __syncwarp();
+  {
+    double* __restrict__ pg = sm.fac_pg[H - 1];
+    const double* __restrict__ nb = sm.nblk[H - 1];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = 2 * cp + j;
+      if (l18) {
+        sm.pm[12 * r6 + c] = qa[j];
+        sm.pm[12 * (6 + r6) + 6 + c] = qc[j];
+        pg[6 * r6 + c] = 0.5 * qa[j];
+        pg[6 * (6 + r6) + c] = qc[j];
+        ms[6 * r6 + c] = 0.25 * qa[j] + qc[j];
+        md[6 * r6 + c] = r6 >= c ? nb[r6 * (r6 + 1) / 2 + c] : nb[c * (c + 1) / 2 + r6];
+      }
+    }
+  }
   __syncwarp();
 #pragma unroll 1
   for (int t = H - 1; t >= 0; --t) {
     double* __restrict__ pg = sm.fac_pg[t];
-    double* __restrict__ md = sm.m6[RM_D];
-    double* __restrict__ ms = sm.m6[RM_S];
-    // (1) PG = P Gam = P[:, :6] / 2 + P[:, 6:];  S = Gam^T P Gam = A/4 + (B + B^T)/2 + C;  D_t unpacked to 6 x 6
-    if (lane < 24) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) pg[6 * k12 + 3 * ch + c] = 0.5 * sm.pm[12 * k12 + 3 * ch + c] + sm.pm[12 * k12 + 6 + 3 * ch + c];
-    }
-    if (lane < 18) {
-      const double* __restrict__ nb = sm.nblk[t];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int c = 2 * cp + j;
-        ms[6 * r6 + c] = 0.25 * sm.pm[12 * r6 + c] + 0.5 * (sm.pm[12 * r6 + 6 + c] + sm.pm[12 * c + 6 + r6]) + sm.pm[12 * (6 + r6) + 6 + c];
-        md[6 * r6 + c] = r6 >= c ? nb[r6 * (r6 + 1) / 2 + c] : nb[c * (c + 1) / 2 + r6];
-      }
-    }
-    __syncwarp();
     // (2) U = D S
-    if (lane < 18) {
+    {
       const double2 o = row_times_cols(md, ms, r6, cp);
-      *reinterpret_cast<double2*>(sm.m6[RM_U] + 6 * r6 + 2 * cp) = o;
+      if (l18) *reinterpret_cast<double2*>(mu + 6 * r6 + 2 * cp) = o;
     }
     __syncwarp();
     // (3) Y = S + S U   (symmetric positive definite)
-    if (lane < 18) {
-      double2 o = row_times_cols(ms, sm.m6[RM_U], r6, cp);
+    {
+      double2 o = row_times_cols(ms, mu, r6, cp);
       const double2 s0 = ldd2(ms + 6 * r6 + 2 * cp);
       o.x += s0.x; o.y += s0.y;
-      *reinterpret_cast<double2*>(sm.m6[RM_Y] + 6 * r6 + 2 * cp) = o;
+      if (l18) *reinterpret_cast<double2*>(my + 6 * r6 + 2 * cp) = o;
     }
     __syncwarp();
     // (4) Y^-1 by 3 x 3 blocks, Y = [[A, B^T], [B, C]]:  G = B A^-1,  Sc = C - G B^T,
-    //     Y^-1 = [[A^-1 + G^T Sc^-1 G, -G^T Sc^-1], [-Sc^-1 G, Sc^-1]].   (4a) G: lanes 0..8, A^-1 redundantly
-    const double* __restrict__ my = sm.m6[RM_Y];
-    double* __restrict__ myi = sm.m6[RM_YI];
-    double* __restrict__ mg = sm.m6[RM_G];
+    //     Y^-1 = [[A^-1 + G^T Sc^-1 G, -G^T Sc^-1], [-Sc^-1 G, Sc^-1]].   (4a) G (lanes 0..8), A^-1 in every lane
     double ai[6];
     bool ok;
     {
-      const double am[6] = {my[0], 0.5 * (my[1] + my[6]), 0.5 * (my[2] + my[12]), my[7], 0.5 * (my[8] + my[13]), my[14]};
+      const double am[6] = {my[0], my[6], my[12], my[7], my[13], my[14]};      // lower triangle of A
       ok = inv3_spd(am, ai);
-    }
-    const int gr = lane < 9 ? lane / 3 : 0, gc = lane < 9 ? lane - 3 * (lane / 3) : 0;
-    if (lane < 9) {
-      // B[r][k] = sym(Y[3 + r][k]);  A^-1 packed (00, 01, 02, 11, 12, 22): column gc = (ai[gc], ...)
-      const double b0 = 0.5 * (my[6 * (3 + gr)] + my[3 + gr]), b1 = 0.5 * (my[6 * (3 + gr) + 1] + my[6 + 3 + gr]),
-                   b2 = 0.5 * (my[6 * (3 + gr) + 2] + my[12 + 3 + gr]);
+      const double b0 = my[6 * (3 + gr)], b1 = my[6 * (3 + gr) + 1], b2 = my[6 * (3 + gr) + 2];   // row gr of B
       const double a0 = gc == 0 ? ai[0] : (gc == 1 ? ai[1] : ai[2]);
       const double a1 = gc == 0 ? ai[1] : (gc == 1 ? ai[3] : ai[4]);
       const double a2 = gc == 0 ? ai[2] : (gc == 1 ? ai[4] : ai[5]);
-      mg[3 * gr + gc] = b0 * a0 + b1 * a1 + b2 * a2;
+      const double g = b0 * a0 + b1 * a1 + b2 * a2;
+      if (l9) mg[3 * gr + gc] = g;
     }
     __syncwarp();
-    // (4b) Sc and Sc^-1 redundantly in every lane; lanes 0..8 write -Sc^-1 G (block 21), lanes 9..17 Sc^-1 (block 22)
+    // (4b) Sc and Sc^-1 in every lane; lanes 0..8 write -Sc^-1 G (blocks 21 and 12), lanes 9..17 Sc^-1 (block 22)
     double sci[6];
     {
-      double g[9], bmat[9];
+      double g[9], bm[9];
 #pragma unroll
       for (int i = 0; i < 9; ++i) g[i] = mg[i];
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) bmat[3 * r + c] = 0.5 * (my[6 * (3 + r) + c] + my[6 * c + 3 + r]);
+        for (int c = 0; c < 3; ++c) bm[3 * r + c] = my[6 * (3 + r) + c];
       double scm[6];
-      scm[0] = my[21] - (g[0] * bmat[0] + g[1] * bmat[1] + g[2] * bmat[2]);
-      scm[1] = 0.5 * (my[22] + my[27]) - (g[0] * bmat[3] + g[1] * bmat[4] + g[2] * bmat[5]);
-      scm[2] = 0.5 * (my[23] + my[33]) - (g[0] * bmat[6] + g[1] * bmat[7] + g[2] * bmat[8]);
-      scm[3] = my[28] - (g[3] * bmat[3] + g[4] * bmat[4] + g[5] * bmat[5]);
-      scm[4] = 0.5 * (my[29] + my[34]) - (g[3] * bmat[6] + g[4] * bmat[7] + g[5] * bmat[8]);
-      scm[5] = my[35] - (g[6] * bmat[6] + g[7] * bmat[7] + g[8] * bmat[8]);
+      scm[0] = my[21] - (g[0] * bm[0] + g[1] * bm[1] + g[2] * bm[2]);
+      scm[1] = my[27] - (g[0] * bm[3] + g[1] * bm[4] + g[2] * bm[5]);
+      scm[2] = my[33] - (g[0] * bm[6] + g[1] * bm[7] + g[2] * bm[8]);
+      scm[3] = my[28] - (g[3] * bm[3] + g[4] * bm[4] + g[5] * bm[5]);
+      scm[4] = my[34] - (g[3] * bm[6] + g[4] * bm[7] + g[5] * bm[8]);
+      scm[5] = my[35] - (g[6] * bm[6] + g[7] * bm[7] + g[8] * bm[8]);
       ok = inv3_spd(scm, sci) && ok;
       if (!ok && lane == 0) sm.flag = 1;
-      if (lane < 9) {
-        // -(Sc^-1 G)[gr][gc]
-        const double s0 = gr == 0 ? sci[0] : (gr == 1 ? sci[1] : sci[2]);
-        const double s1 = gr == 0 ? sci[1] : (gr == 1 ? sci[3] : sci[4]);
-        const double s2 = gr == 0 ? sci[2] : (gr == 1 ? sci[4] : sci[5]);
-        const double v = -(s0 * mg[gc] + s1 * mg[3 + gc] + s2 * mg[6 + gc]);
-        myi[6 * (3 + gr) + gc] = v;
-        myi[6 * gc + 3 + gr] = v;
-      } else if (lane < 18) {
-        const int r = (lane - 9) / 3, c = (lane - 9) - 3 * r;
-        myi[6 * (3 + r) + 3 + c] = pick_sym3(sci, r, c);
-      }
+      const double s0 = gr == 0 ? sci[0] : (gr == 1 ? sci[1] : sci[2]);
+      const double s1 = gr == 0 ? sci[1] : (gr == 1 ? sci[3] : sci[4]);
+      const double s2 = gr == 0 ? sci[2] : (gr == 1 ? sci[4] : sci[5]);
+      const double v21 = -(s0 * mg[gc] + s1 * mg[3 + gc] + s2 * mg[6 + gc]);   // -(Sc^-1 G)[gr][gc]
+      const double v22 = pick_sym3(sci, r22, c22);
+      if (l9) { myi[6 * (3 + gr) + gc] = v21; myi[6 * gc + 3 + gr] = v21; }
+      if (l22) myi[6 * (3 + r22) + 3 + c22] = v22;
     }
     __syncwarp();
     // (4c) block 11: A^-1 - G^T Y21   (Y21 = -Sc^-1 G just written)
-    if (lane < 9) {
-      const double a = pick_sym3(ai, gr, gc);
-      myi[6 * gr + gc] = a - (mg[gr] * myi[18 + gc] + mg[3 + gr] * myi[24 + gc] + mg[6 + gr] * myi[30 + gc]);
+    {
+      const double v11 = pick_sym3(ai, gr, gc) - (mg[gr] * myi[18 + gc] + mg[3 + gr] * myi[24 + gc] + mg[6 + gr] * myi[30 + gc]);
+      if (l9) myi[6 * gr + gc] = v11;
     }
     __syncwarp();
     // (5) J = S Y^-1
-    if (lane < 18) {
+    {
       const double2 o = row_times_cols(ms, myi, r6, cp);
-      *reinterpret_cast<double2*>(sm.fac_j[t] + 6 * r6 + 2 * cp) = o;
+      if (l18) *reinterpret_cast<double2*>(sm.fac_j[t] + 6 * r6 + 2 * cp) = o;
     }
     __syncwarp();
     // (6) N = D J
-    if (lane < 18) {
+    {
       const double2 o = row_times_cols(md, sm.fac_j[t], r6, cp);
-      *reinterpret_cast<double2*>(sm.fac_n[t] + 6 * r6 + 2 * cp) = o;
+      if (l18) *reinterpret_cast<double2*>(sm.fac_n[t] + 6 * r6 + 2 * cp) = o;
     }
     if (t == 0) break;                       // P_0 is never needed: x_0 = 0
     __syncwarp();
-    // (7) T1 = PG N   (12 x 6; N symmetrised on the fly)
-    if (lane < 24) {
-      const double* __restrict__ nn = sm.fac_n[t];
-      double pr[6];
+    // (7) T1 = PG N   (12 x 6): lane (k12, ch) computes columns 3 ch .. 3 ch + 2 of row k12
+    {
+      const double* __restrict__ nn = sm.fac_n[t] + 3 * ch;
+      const double2 p01 = ldd2(pg + 6 * k12), p23 = ldd2(pg + 6 * k12 + 2), p45 = ldd2(pg + 6 * k12 + 4);
+      double v[3];
 #pragma unroll
-      for (int j = 0; j < 6; ++j) pr[j] = pg[6 * k12 + j];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int cc = 3 * ch + c;
-        double v = 0.0;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) v = fma(pr[j], 0.5 * (nn[6 * j + cc] + nn[6 * cc + j]), v);
-        sm.t1[6 * k12 + cc] = v;
-      }
+      for (int c = 0; c < 3; ++c)
+        v[c] = (p01.x * nn[c] + p01.y * nn[6 + c] + p23.x * nn[12 + c]) + (p23.y * nn[18 + c] + p45.x * nn[24 + c] + p45.y * nn[30 + c]);
+      if (l24) { sm.t1[6 * k12 + 3 * ch] = v[0]; sm.t1[6 * k12 + 3 * ch + 1] = v[1]; sm.t1[6 * k12 + 3 * ch + 2] = v[2]; }
     }
     __syncwarp();
-    // (8) P' = P - T1 PG^T: lower triangle, mirrored into pm2
+    // (8) P' = P - T1 PG^T: lower triangle (78 entries, <= 3 per lane), mirrored into pm2
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const int k = pk[i], l = pl[i];
-      if (k >= 0) {
-        const double2 t01 = ldd2(sm.t1 + 6 * k), t23 = ldd2(sm.t1 + 6 * k + 2), t45 = ldd2(sm.t1 + 6 * k + 4);
-        const double2 g01 = ldd2(pg + 6 * l), g23 = ldd2(pg + 6 * l + 2), g45 = ldd2(pg + 6 * l + 4);
-        const double v = sm.pm[12 * k + l] - ((t01.x * g01.x + t01.y * g01.y + t23.x * g23.x) + (t23.y * g23.y + t45.x * g45.x + t45.y * g45.y));
-        sm.pm2[12 * k + l] = v;
-        sm.pm2[12 * l + k] = v;
-      }
+      const double2 t01 = ldd2(sm.t1 + 6 * k), t23 = ldd2(sm.t1 + 6 * k + 2), t45 = ldd2(sm.t1 + 6 * k + 4);
+      const double2 g01 = ldd2(pg + 6 * l), g23 = ldd2(pg + 6 * l + 2), g45 = ldd2(pg + 6 * l + 4);
+      const double v = sm.pm[12 * k + l] - ((t01.x * g01.x + t01.y * g01.y + t23.x * g23.x) + (t23.y * g23.y + t45.x * g45.x + t45.y * g45.y));
+      if (lane + 32 * i < 78) { sm.pm2[12 * k + l] = v; sm.pm2[12 * l + k] = v; }
     }
     __syncwarp();
-    // (9) P_t = Q + Phi^T P' Phi:  A_t = A' + K2,  B_t = A' + B',  C_t = A' + B' + B'^T + C' + K1
-    if (lane < 18) {
+    // (9) P_t = Q + Phi^T P' Phi:  A_t = A' + K2,  B_t = A' + B',  C_t = A' + B' + B'^T + C' + K1 -- and, from the same
+    //     four entries, the inputs of the next stage:  PG = P_t Gam,  S = Gam^T P_t Gam;  D_{t-1} unpacked
+    {
+      double* __restrict__ pgn = sm.fac_pg[t - 1];
+      const double* __restrict__ nb = sm.nblk[t - 1];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int r = r6, c = 2 * cp + j;
         const double a = sm.pm2[12 * r + c], bb = sm.pm2[12 * r + 6 + c], bt = sm.pm2[12 * c + 6 + r], cc = sm.pm2[12 * (6 + r) + 6 + c];
-        double qa = 0.0, qc = 0.0;
-        if (r < 3 && c < 3) qa = sm.k2ang[3 * r + c];
-        else if (r == c) qa = sm.k2lin[r - 3];
-        if (r == c) qc = sm.k1[r];
-        sm.pm[12 * r + c] = a + qa;
-        sm.pm[12 * r + 6 + c] = a + bb;
-        sm.pm[12 * (6 + c) + r] = a + bb;
-        sm.pm[12 * (6 + r) + 6 + c] = a + bb + bt + cc + qc;
+        const double at = a + qa[j], brc = a + bb, bcr = a + bt, ct = a + bb + bt + cc + qc[j];
+        const double dv = r >= c ? nb[r * (r + 1) / 2 + c] : nb[c * (c + 1) / 2 + r];
+        if (l18) {
+          sm.pm[12 * r + c] = at;
+          sm.pm[12 * r + 6 + c] = brc;
+          sm.pm[12 * (6 + c) + r] = brc;
+          sm.pm[12 * (6 + r) + 6 + c] = ct;
+          pgn[6 * r + c] = 0.5 * at + brc;
+          pgn[6 * (6 + r) + c] = 0.5 * bcr + ct;
+          ms[6 * r + c] = 0.25 * at + 0.5 * (brc + bcr) + ct;
+          md[6 * r + c] = dv;
+        }
       }
     }
     __syncwarp();
@@ -1484,6 +1485,10 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
   // through to the interior point untouched.
   const int cold_rounds = ws->cold_start_rounds;
   const double cold_max_viol = (double)ws->cold_start_max_violations;
+  // Weakly active rows (multiplier ~ 0 at the optimum: strict complementarity fails) flip for ever between "dropped
+  // because its multiplier is -1e-10" and "violated by 1e-9 without it".  A row that was dropped and came back is
+  // sticky: it then only leaves for a multiplier that is wrong by more than 1e-7 of the gradient scale.
+  unsigned dropped_rows = 0u, sticky_rows = 0u;
 #pragma unroll 1
   for (int attempt = (cold_rounds > 0 && !skip_cold) ? -1 : 0; attempt < (LEAN ? 0 : 3) && !done; ++attempt) {
     bool converged = false, ipm_dead = false, handed_over = false;
@@ -1816,7 +1821,10 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
               else act_new |= 1u << r;
             }
           }
-          if (rworst >= 0) act_new |= 1u << rworst;
+          if (rworst >= 0) {
+            act_new |= 1u << rworst;
+            if ((dropped_rows >> rworst) & 1u) sticky_rows |= 1u << rworst;
+          }
           // multipliers: sum_i y_i a_i = -gr on span(e)
           double y[3] = {0, 0, 0};
 #pragma unroll 1
@@ -1831,7 +1839,8 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
           for (int i = 0; i < na; ++i) {
             // upper-bound rows need y >= 0, lower-bound rows y <= 0
             const double ysgn = rows[i] < 5 ? y[i] : -y[i];
-            if (ysgn < -1e-10 * qscale) act_new &= ~(1u << rows[i]);
+            const double drop_tol = ((sticky_rows >> rows[i]) & 1u) ? 1e-7 : 1e-10;
+            if (ysgn < -drop_tol * qscale) { act_new &= ~(1u << rows[i]); dropped_rows |= 1u << rows[i]; }
             if (ysgn < ymin) { ymin = ysgn; imin = i; }
           }
           // a block that already holds three rows is a vertex: a violated fourth row can only come in if one

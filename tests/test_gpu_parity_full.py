@@ -403,3 +403,15 @@ def test_standalone_estimator_swing_and_pack_entry_points(rg_lib, cuda_device):
             else:
                 exp = (0.0, 0.0, 0.0, 0.0, torques[e, m])
             assert tuple(a[e, m]) == tuple(np.float32(x) for x in exp), (e, m)
+
+
+def test_weakly_active_row_does_not_cycle(rg_lib, cuda_device):
+    """Env 17809 of the prefix-stable batch has a friction row whose multiplier is -1.7e-10 at the optimum (no strict
+    complementarity): the active-set rounds used to flip it in and out until the budget ran out (status: interior point
+    only).  Rows that come back after being dropped are now sticky; the solve must verify and match the oracle."""
+    st = synthetic.make_states_sharded(17809 - 3, 17809 + 3, GHOST)
+    for two in (0, 1):
+        f, hf, info, _ = _solve(cuda_device, st, want_horizon=True, two_kernel_solve=two)
+        assert np.all(info[:, rg.RG_INFO_STATUS] & rg.RG_STATUS_POLISHED), info
+        ref = _numpy_oracle(st, 3, 10)
+        assert np.abs(hf[3].reshape(-1) - ref).max() < REL_TOL * max(1.0, np.abs(ref).max())

@@ -28,6 +28,14 @@ f, hf, info = rg.mpc_build_solve(ws, t(st.com_velocity_body), t(st.base_rpy), t(
 torch.cuda.synchronize()
 inf = info.cpu().numpy()
 print("bound ok", np.isfinite(f.cpu().numpy()).all(), "interior-point envs", int((inf[:, 0] > 0).sum()), "of", n)
+# the two-kernel path (lean kernel + fallback queue) needs more envs than fit one wave
+big = int(os.environ.get("RG_SANITIZE_BIG", "1600"))
+ws = rg.MpcWorkspace(p, max_envs=big)
+st = synthetic.make_states(big, pace, seed=6)
+f, hf, info = rg.mpc_build_solve(ws, t(st.com_velocity_body), t(st.base_rpy), t(st.base_rpy_rate), t(st.planned_contacts), t(st.foot_positions_base), t(st.command))
+torch.cuda.synchronize()
+inf = info.cpu().numpy()
+print("two-kernel bound ok", np.isfinite(f.cpu().numpy()).all(), "queued envs", int(((inf[:, 2] & 16) == 0).sum()), "of", big)
 st = synthetic.make_states(n, GHOST, seed=3)
 robot = SyntheticRobotBatch(GHOST, st)
 ctl = BatchedMPCController(robot, robot.GetTimeSinceReset)
