@@ -104,6 +104,13 @@ struct Cfg {
 #define RG_MIN_BLOCKS_H20 4
 #endif
   static constexpr bool RICCATI = H >= RG_RICCATI_MIN_H;
+  // active-set basis of a block in named registers (no local-memory frame: DRAM traffic = algorithmic bytes) or in small
+  // local arrays (fewer live registers across the heavy phases).  Registers win at h = 10 (4096 envs +1 %, 65536 envs -3 %,
+  // DRAM traffic 3.2 -> 0.6 MB per 4096-env launch); at h = 5 / 20 the extra spills cost 7-9 % (profiles/r02_basis_storage.md).
+#ifndef RG_BASIS_IN_REGS_H10
+#define RG_BASIS_IN_REGS_H10 1
+#endif
+  static constexpr bool BASIS_IN_REGS = (H == 10) && RG_BASIS_IN_REGS_H10;
   static constexpr int CHOL_W = (H == 10) ? RG_CHOL_W_H10 : 4;
   static constexpr int MIN_BLOCKS = H <= 5 ? RG_MIN_BLOCKS_H5 : (H <= 10 ? RG_MIN_BLOCKS_H10 : (RICCATI ? RG_MIN_BLOCKS_H20 : 2));
 };
@@ -1153,6 +1160,58 @@ __device__ __forceinline__ void chol5_block_solve(const Chol5& c, const double* 
   for (int i = 0; i < 5; ++i) c5[i] = z[i] * inv_d[i];
 }
 
+// Orthonormal basis of the active normals of one (step, leg) block (Gram-Schmidt in bit order, at most three rows):
+//   a_i = sum_k rr[k][i] e_k,  targets bt_i,  row ids;  dependent normals and rows beyond the third are cleared from act.
+// Everything lives in named registers (slot 0 / 1 / 2 chosen by predication): indexing small arrays with the run-time
+// count put them into a 480-byte local-memory frame per thread whose write-back was most of the kernel's DRAM traffic.
+// Built twice per round from the same bit mask -- before the factorisation (particular solution, projector) and in the
+// verification (multipliers) -- instead of being kept live across the heavy phases: 21 doubles fewer in flight.
+struct BlockBasis {
+  double e0[3], e1[3], e2[3];
+  double r00, r01, r02, r11, r12, r22;
+  double bt0, bt1, bt2;
+  int row0, row1, row2, na;
+};
+
+__device__ __forceinline__ void build_basis(unsigned& act, bool active_blk, const double* mu, const double* hv_up, const double* lo_b,
+                                            BlockBasis& B) {
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { B.e0[d] = 0.0; B.e1[d] = 0.0; B.e2[d] = 0.0; }
+  B.r00 = 1.0; B.r01 = 0.0; B.r02 = 0.0; B.r11 = 1.0; B.r12 = 0.0; B.r22 = 1.0;
+  B.bt0 = B.bt1 = B.bt2 = 0.0;
+  B.row0 = B.row1 = B.row2 = -1;
+  B.na = 0;
+  if (!active_blk) return;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    if (((act >> r) & 1u) && B.na < 3) {
+      const int rw = r < 5 ? r : r - 5;                                  // compile-time: the loop is unrolled
+      double a0 = rw == 0 ? -1.0 : (rw == 1 ? 1.0 : 0.0), a1 = rw == 2 ? -1.0 : (rw == 3 ? 1.0 : 0.0), a2 = rw < 4 ? mu[rw] : 1.0;
+      const double target = r < 5 ? hv_up[rw] : lo_b[rw];
+      const double c0 = B.na > 0 ? a0 * B.e0[0] + a1 * B.e0[1] + a2 * B.e0[2] : 0.0;
+      a0 -= c0 * B.e0[0]; a1 -= c0 * B.e0[1]; a2 -= c0 * B.e0[2];
+      const double c1 = B.na > 1 ? a0 * B.e1[0] + a1 * B.e1[1] + a2 * B.e1[2] : 0.0;
+      a0 -= c1 * B.e1[0]; a1 -= c1 * B.e1[1]; a2 -= c1 * B.e1[2];
+      const double nrm = sqrt(a0 * a0 + a1 * a1 + a2 * a2);
+      if (nrm < 1e-9) {
+        act &= ~(1u << r);                                               // dependent normal: drop
+      } else {
+        const double inrm = 1.0 / nrm;
+        if (B.na == 0) { B.e0[0] = a0 * inrm; B.e0[1] = a1 * inrm; B.e0[2] = a2 * inrm; B.r00 = nrm; B.bt0 = target; B.row0 = r; }
+        else if (B.na == 1) { B.e1[0] = a0 * inrm; B.e1[1] = a1 * inrm; B.e1[2] = a2 * inrm; B.r01 = c0; B.r11 = nrm; B.bt1 = target; B.row1 = r; }
+        else { B.e2[0] = a0 * inrm; B.e2[1] = a1 * inrm; B.e2[2] = a2 * inrm; B.r02 = c0; B.r12 = c1; B.r22 = nrm; B.bt2 = target; B.row2 = r; }
+        ++B.na;
+      }
+    }
+  }
+  // rows beyond the third independent one cannot be held: drop them from the guess
+  unsigned keep = 0u;
+  if (B.row0 >= 0) keep |= 1u << B.row0;
+  if (B.row1 >= 0) keep |= 1u << B.row1;
+  if (B.row2 >= 0) keep |= 1u << B.row2;
+  act &= keep;
+}
+
 // One env's stance QP, executed by the whole CTA.
 // LEAN = true : the verified active-set rounds only -- no interior-point state or code (the registers that frees
 //               are most of the kernel's local-memory frame).  An env whose rounds do not verify within the
@@ -1683,59 +1742,92 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
 #pragma unroll 1
     for (int round = 0; round < round_budget; ++round) {
       ++polish_rounds;
-      // --- per block: orthonormal basis of the active normals (<= 3), null-space basis Z, u0
-      double e[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-      double rr[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};   // a_i = sum_k rr[k][i] e_k
-      double bt[3] = {0, 0, 0};
+      // --- per block: orthonormal basis of the active normals (<= 3), null-space basis Z, u0.
+      // Two storage schemes, chosen per horizon by measurement (profiles/r02_basis_storage.md): named registers
+      // (Cfg::BASIS_IN_REGS: no local-memory frame, DRAM traffic = the algorithmic bytes) or small local arrays indexed
+      // by the run-time row count (fewer live registers across the heavy phases, but a 480-byte frame per thread).
+      int na;
+      double u0[3], mproj[6];
+      BlockBasis B;                                                        // register scheme
+      double e[3][3], rr[3][3];                                            // array scheme: a_i = sum_k rr[k][i] e_k
       int rows[3] = {-1, -1, -1};
-      int na = 0;
-      if (active_blk) {
+      if constexpr (C::BASIS_IN_REGS) {
+        {
+          build_basis(act, active_blk, mu, hv_up, lo_b, B);
+          na = B.na;
+          // particular solution u0 = sum_k c_k e_k with a_i . u0 = b_i  (forward substitution with rr^T; unused slots have
+          // zero basis vectors and unit diagonal, so they contribute nothing)
+          const double cp0 = na > 0 ? B.bt0 / B.r00 : 0.0;
+          const double cp1 = na > 1 ? (B.bt1 - B.r01 * cp0) / B.r11 : 0.0;
+          const double cp2 = na > 2 ? (B.bt2 - B.r02 * cp0 - B.r12 * cp1) / B.r22 : 0.0;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) u0[d] = cp0 * B.e0[d] + cp1 * B.e1[d] + cp2 * B.e2[d];
+          // projector onto the free directions  M = I - sum_k e_k e_k^T, packed (xx,yy,zz,xz,yz,xy),
+          // scaled by 1 / (2 alpha): this is the "E^-1" of the equality-constrained Newton system
+          mproj[0] = 1.0 - (B.e0[0] * B.e0[0] + B.e1[0] * B.e1[0] + B.e2[0] * B.e2[0]);
+          mproj[1] = 1.0 - (B.e0[1] * B.e0[1] + B.e1[1] * B.e1[1] + B.e2[1] * B.e2[1]);
+          mproj[2] = 1.0 - (B.e0[2] * B.e0[2] + B.e1[2] * B.e1[2] + B.e2[2] * B.e2[2]);
+          mproj[3] = -(B.e0[0] * B.e0[2] + B.e1[0] * B.e1[2] + B.e2[0] * B.e2[2]);
+          mproj[4] = -(B.e0[1] * B.e0[2] + B.e1[1] * B.e1[2] + B.e2[1] * B.e2[2]);
+          mproj[5] = -(B.e0[0] * B.e0[1] + B.e1[0] * B.e1[1] + B.e2[0] * B.e2[1]);
+        }
+
+      } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { e[i][k] = 0.0; rr[i][k] = 0.0; }
+        double bt[3] = {0, 0, 0};
+        na = 0;
+        if (active_blk) {
 #pragma unroll 1
-        for (int r = 0; r < 10; ++r) {
-          if (!((act >> r) & 1u) || na >= 3) continue;
-          const int rw = r < 5 ? r : r - 5;
-          double a[3] = {rw == 0 ? -1.0 : rw == 1 ? 1.0 : 0.0, rw == 2 ? -1.0 : rw == 3 ? 1.0 : 0.0,
-                         rw < 4 ? mu[rw] : 1.0};
-          const double target = r < 5 ? hv_up[rw] : lo_b[rw];
-          double coef[3] = {0, 0, 0};
-          for (int k = 0; k < na; ++k) {
-            coef[k] = a[0] * e[k][0] + a[1] * e[k][1] + a[2] * e[k][2];
-            a[0] -= coef[k] * e[k][0]; a[1] -= coef[k] * e[k][1]; a[2] -= coef[k] * e[k][2];
+          for (int r = 0; r < 10; ++r) {
+            if (!((act >> r) & 1u) || na >= 3) continue;
+            const int rw = r < 5 ? r : r - 5;
+            double a[3] = {rw == 0 ? -1.0 : rw == 1 ? 1.0 : 0.0, rw == 2 ? -1.0 : rw == 3 ? 1.0 : 0.0,
+                           rw < 4 ? mu[rw] : 1.0};
+            const double target = r < 5 ? hv_up[rw] : lo_b[rw];
+            double coef[3] = {0, 0, 0};
+            for (int k = 0; k < na; ++k) {
+              coef[k] = a[0] * e[k][0] + a[1] * e[k][1] + a[2] * e[k][2];
+              a[0] -= coef[k] * e[k][0]; a[1] -= coef[k] * e[k][1]; a[2] -= coef[k] * e[k][2];
+            }
+            const double nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+            if (nrm < 1e-9) { act &= ~(1u << r); continue; }   // dependent normal: drop
+            const double inrm = 1.0 / nrm;
+            e[na][0] = a[0] * inrm; e[na][1] = a[1] * inrm; e[na][2] = a[2] * inrm;
+            for (int k = 0; k < na; ++k) rr[k][na] = coef[k];
+            rr[na][na] = nrm;
+            bt[na] = target;
+            rows[na] = r;
+            ++na;
           }
-          const double nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-          if (nrm < 1e-9) { act &= ~(1u << r); continue; }   // dependent normal: drop
-          const double inrm = 1.0 / nrm;
-          e[na][0] = a[0] * inrm; e[na][1] = a[1] * inrm; e[na][2] = a[2] * inrm;
-          for (int k = 0; k < na; ++k) rr[k][na] = coef[k];
-          rr[na][na] = nrm;
-          bt[na] = target;
-          rows[na] = r;
-          ++na;
+          // rows beyond the third independent one cannot be held: drop them from the guess
+#pragma unroll 1
+          for (int r = 0; r < 10; ++r) {
+            if (((act >> r) & 1u) && r != rows[0] && r != rows[1] && r != rows[2]) act &= ~(1u << r);
+          }
         }
-        // rows beyond the third independent one cannot be held: drop them from the guess
+        // particular solution u0 = sum_k c_k e_k with a_i . u0 = b_i
+        double cpar[3] = {0, 0, 0};
 #pragma unroll 1
-        for (int r = 0; r < 10; ++r) {
-          if (((act >> r) & 1u) && r != rows[0] && r != rows[1] && r != rows[2]) act &= ~(1u << r);
+        for (int i = 0; i < na; ++i) {
+          double v = bt[i];
+          for (int k = 0; k < i; ++k) v -= rr[k][i] * cpar[k];
+          cpar[i] = v / rr[i][i];
         }
-      }
-      // particular solution u0 = sum_k c_k e_k with a_i . u0 = b_i
-      double cpar[3] = {0, 0, 0};
+        u0[0] = u0[1] = u0[2] = 0.0;
 #pragma unroll 1
-      for (int i = 0; i < na; ++i) {
-        double v = bt[i];
-        for (int k = 0; k < i; ++k) v -= rr[k][i] * cpar[k];
-        cpar[i] = v / rr[i][i];
-      }
-      double u0[3] = {0, 0, 0};
+        for (int k = 0; k < na; ++k) { u0[0] += cpar[k] * e[k][0]; u0[1] += cpar[k] * e[k][1]; u0[2] += cpar[k] * e[k][2]; }
+        // projector onto the free directions  M = I - sum_k e_k e_k^T, packed (xx,yy,zz,xz,yz,xy),
+        // scaled by 1 / (2 alpha): this is the "E^-1" of the equality-constrained Newton system
+        mproj[0] = mproj[1] = mproj[2] = 1.0; mproj[3] = mproj[4] = mproj[5] = 0.0;
 #pragma unroll 1
-      for (int k = 0; k < na; ++k) { u0[0] += cpar[k] * e[k][0]; u0[1] += cpar[k] * e[k][1]; u0[2] += cpar[k] * e[k][2]; }
-      // projector onto the free directions  M = I - sum_k e_k e_k^T, packed (xx,yy,zz,xz,yz,xy),
-      // scaled by 1 / (2 alpha): this is the "E^-1" of the equality-constrained Newton system
-      double mproj[6] = {1.0, 1.0, 1.0, 0.0, 0.0, 0.0};
-#pragma unroll 1
-      for (int k = 0; k < na; ++k) {
-        mproj[0] -= e[k][0] * e[k][0]; mproj[1] -= e[k][1] * e[k][1]; mproj[2] -= e[k][2] * e[k][2];
-        mproj[3] -= e[k][0] * e[k][2]; mproj[4] -= e[k][1] * e[k][2]; mproj[5] -= e[k][0] * e[k][1];
+        for (int k = 0; k < na; ++k) {
+          mproj[0] -= e[k][0] * e[k][0]; mproj[1] -= e[k][1] * e[k][1]; mproj[2] -= e[k][2] * e[k][2];
+          mproj[3] -= e[k][0] * e[k][2]; mproj[4] -= e[k][1] * e[k][2]; mproj[5] -= e[k][0] * e[k][1];
+        }
+
       }
       if (na == 3 || !active_blk) { mproj[0] = mproj[1] = mproj[2] = mproj[3] = mproj[4] = mproj[5] = 0.0; }
       const double inv2a = 1.0 / two_alpha;
@@ -1825,28 +1917,56 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
             act_new |= 1u << rworst;
             if ((dropped_rows >> rworst) & 1u) sticky_rows |= 1u << rworst;
           }
-          // multipliers: sum_i y_i a_i = -gr on span(e)
-          double y[3] = {0, 0, 0};
+          int rmin = -1;
+          if constexpr (C::BASIS_IN_REGS) {
+            // multipliers: sum_i y_i a_i = -gr on span(e)  ->  back substitution with the upper triangular rr
+            const int row0 = B.row0, row1 = B.row1, row2 = B.row2;
+            const double g0 = -(gr[0] * B.e0[0] + gr[1] * B.e0[1] + gr[2] * B.e0[2]);
+            const double g1 = -(gr[0] * B.e1[0] + gr[1] * B.e1[1] + gr[2] * B.e1[2]);
+            const double g2 = -(gr[0] * B.e2[0] + gr[1] * B.e2[1] + gr[2] * B.e2[2]);
+            const double y2 = g2 / B.r22;
+            const double y1 = (g1 - B.r12 * y2) / B.r11;
+            const double y0 = (g0 - B.r01 * y1 - B.r02 * y2) / B.r00;
+            double ymin = 1e300;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const int row = i == 0 ? row0 : (i == 1 ? row1 : row2);
+              const double yi = i == 0 ? y0 : (i == 1 ? y1 : y2);
+              if (i < na) {
+                // upper-bound rows need y >= 0, lower-bound rows y <= 0
+                const double ysgn = row < 5 ? yi : -yi;
+                const double drop_tol = ((sticky_rows >> row) & 1u) ? 1e-7 : 1e-10;
+                if (ysgn < -drop_tol * qscale) { act_new &= ~(1u << row); dropped_rows |= 1u << row; }
+                if (ysgn < ymin) { ymin = ysgn; rmin = row; }
+              }
+            }
+
+          } else {
+            // multipliers: sum_i y_i a_i = -gr on span(e)
+            double y[3] = {0, 0, 0};
 #pragma unroll 1
-          for (int i = na - 1; i >= 0; --i) {
-            double v = -(gr[0] * e[i][0] + gr[1] * e[i][1] + gr[2] * e[i][2]);
-            for (int k = i + 1; k < na; ++k) v -= rr[i][k] * y[k];
-            y[i] = v / rr[i][i];
-          }
-          double ymin = 1e300;
-          int imin = -1;
+            for (int i = na - 1; i >= 0; --i) {
+              double v = -(gr[0] * e[i][0] + gr[1] * e[i][1] + gr[2] * e[i][2]);
+              for (int k = i + 1; k < na; ++k) v -= rr[i][k] * y[k];
+              y[i] = v / rr[i][i];
+            }
+            double ymin = 1e300;
+            int imin = -1;
 #pragma unroll 1
-          for (int i = 0; i < na; ++i) {
-            // upper-bound rows need y >= 0, lower-bound rows y <= 0
-            const double ysgn = rows[i] < 5 ? y[i] : -y[i];
-            const double drop_tol = ((sticky_rows >> rows[i]) & 1u) ? 1e-7 : 1e-10;
-            if (ysgn < -drop_tol * qscale) { act_new &= ~(1u << rows[i]); dropped_rows |= 1u << rows[i]; }
-            if (ysgn < ymin) { ymin = ysgn; imin = i; }
+            for (int i = 0; i < na; ++i) {
+              // upper-bound rows need y >= 0, lower-bound rows y <= 0
+              const double ysgn = rows[i] < 5 ? y[i] : -y[i];
+              const double drop_tol = ((sticky_rows >> rows[i]) & 1u) ? 1e-7 : 1e-10;
+              if (ysgn < -drop_tol * qscale) { act_new &= ~(1u << rows[i]); dropped_rows |= 1u << rows[i]; }
+              if (ysgn < ymin) { ymin = ysgn; imin = i; }
+            }
+
+            rmin = imin >= 0 ? rows[imin] : -1;
           }
           // a block that already holds three rows is a vertex: a violated fourth row can only come in if one
           // leaves, and the basis builder keeps the first three in bit order -- without this swap the newcomer
           // is dropped again next round and the same round repeats for ever.  The weakest multiplier leaves.
-          if (na == 3 && (act_new & ~act) != 0u && (act_new & act) == act) act_new &= ~(1u << rows[imin]);
+          if (na == 3 && (act_new & ~act) != 0u && (act_new & act) == act) act_new &= ~(1u << rmin);
         }
         // stationarity on the free subspace is what the solve is supposed to deliver; check it anyway so
         // that a wrong factorisation can never be reported as a verified optimum:  |Z Z^T (P u + q)|_inf
