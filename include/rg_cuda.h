@@ -126,7 +126,7 @@ int rg_mpc_release(const void* workspace);
  *                                   of this entry point (or of robot_gym.cuda.mpc_build_solve) must do so too
  *   base_rpy_rate      [N,3]  f32   Robot.GetBaseRollPitchYawRate (robot.py:205-213)
  *   foot_contact_state [N,4]  u8    1 = planned stance (held over the horizon); 4-byte aligned
- *   foot_positions_base[N,12] f32   Robot.GetFootPositionsInBaseFrame (robot.py:389-397)
+ *   foot_positions_base[N,12] f32   Robot.GetFootPositionsInBaseFrame (robot.py:389-397); 16-byte aligned
  *   command            [N,3]  f32   desired (vx, vy, wz) incl. per-robot offsets
  *   com_height         [N]    f32   or NULL -> EstimateCoMHeightSimple from the stance feet
  *   contact_forces     [N,12] f32   OUT  -(first-step QP solution): force applied ON the ground
@@ -290,8 +290,10 @@ int rg_pack_hybrid_action(const void* robot_workspace, int n_env, const int32_t*
                           const float* swing_joint_angles, const uint8_t* swing_joint_valid,
                           const float* motor_torques, float* action, void* stream);
 
-/* Fused control step = MPCController.get_action() (mpc_controller.py:102-106): gait update,
- * velocity estimator, swing latch/target/IK, MPC stance solve, force->torque, action pack.
+/* One call = MPCController.get_action() (mpc_controller.py:102-106): gait update, velocity estimator, swing
+ * latch/target/IK (prologue kernel), MPC stance solve (one kernel when the batch fits a wave, else the lean kernel plus
+ * the fallback kernel on its queue), force->torque + action pack (+ optional motor model; epilogue kernel): three or
+ * four launches, or ONE graph launch through rg_control_step_graph_* below.
  * All state in/out arrays as in the individual calls.  `controller_state` groups them. */
 typedef struct rg_controller_state {
   /* inputs (robot callbacks) */

@@ -312,6 +312,10 @@ extern "C" int rg_mpc_build_solve_io(const void* workspace, int n_env, const rg_
     rg_set_error("rg_mpc_build_solve: foot_contact_state must be 4-byte aligned");
     return RG_ERR_BAD_ARG;
   }
+  if (((uintptr_t)io->foot_positions_base & 15u) != 0) {  // ... and the twelve foot coordinates with three 128-bit loads
+    rg_set_error("rg_mpc_build_solve: foot_positions_base must be 16-byte aligned");
+    return RG_ERR_BAD_ARG;
+  }
   RgMpcHostInfo info;
   int rc = rg_mpc_workspace_info(workspace, &info);
   if (rc != RG_OK) return rc;

@@ -122,12 +122,13 @@ struct Smem {
   double kinv_ang[RIC ? 1 : Cfg<H>::NKA];    // K^-1 angular block, packed, index a = 3 j + c
   double rdiag[RIC ? 1 : Cfg<H>::N6];
   // Riccati path (see riccati_factor): per stage P_{t+1} Gam (12 x 6), J_t, N_t (6 x 6), and the sweep's scratch
-  __align__(16) double fac_pg[RIC ? H : 1][72];
-  __align__(16) double fac_j[RIC ? H : 1][36];
-  __align__(16) double fac_n[RIC ? H : 1][36];
+  // (the dense path declares them with one or two elements: they must not cost it shared memory)
+  __align__(16) double fac_pg[RIC ? H : 1][RIC ? 72 : 2];
+  __align__(16) double fac_j[RIC ? H : 1][RIC ? 36 : 2];
+  __align__(16) double fac_n[RIC ? H : 1][RIC ? 36 : 2];
   __align__(16) double pm[RIC ? 144 : 2];      // P_{t+1}: full symmetric storage, row-major 12 x 12, order (pi; sigma)
   __align__(16) double pm2[RIC ? 144 : 2];     // P_{t+1} - PG N PG^T before the time update
-  __align__(16) double m6[RIC ? 6 : 1][36];    // 6 x 6 scratch matrices: D, S, U = D S, Y, Y^-1, G
+  __align__(16) double m6[RIC ? 6 : 1][RIC ? 36 : 2];    // 6 x 6 scratch matrices: D, S, U = D S, Y, Y^-1, G
   __align__(16) double t1[RIC ? 72 : 2];       // PG N
   double rvec[RIC ? H * 6 : 1];                // r_t of the backward sweep of the current solve
   double gt[H * 6];                // g~ : gradient in acceleration space
@@ -1273,9 +1274,15 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
   // every load is issued here, before anything depends on one of them: one DRAM latency, not four
   const unsigned contact_word = *reinterpret_cast<const unsigned*>(g_contacts + 4 * (size_t)env);
   const float in_roll = g_rpy[3 * (size_t)env + 0], in_pitch = g_rpy[3 * (size_t)env + 1], in_yaw = g_rpy[3 * (size_t)env + 2];
+  // the twelve foot coordinates of an env are 48 contiguous, 16-byte aligned bytes: three 128-bit loads
   float in_feet[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) in_feet[i] = g_feet[12 * (size_t)env + i];
+  {
+    const float4* __restrict__ f4 = reinterpret_cast<const float4*>(g_feet + 12 * (size_t)env);
+    const float4 fa = f4[0], fb = f4[1], fc = f4[2];
+    in_feet[0] = fa.x; in_feet[1] = fa.y; in_feet[2] = fa.z; in_feet[3] = fa.w;
+    in_feet[4] = fb.x; in_feet[5] = fb.y; in_feet[6] = fb.z; in_feet[7] = fb.w;
+    in_feet[8] = fc.x; in_feet[9] = fc.y; in_feet[10] = fc.z; in_feet[11] = fc.w;
+  }
   const float in_com_h = g_com_height ? g_com_height[env] : 0.f;
   const float in_w[3] = {g_rpy_rate[3 * (size_t)env + 0], g_rpy_rate[3 * (size_t)env + 1], g_rpy_rate[3 * (size_t)env + 2]};
   const float in_v[3] = {g_com_vel[3 * (size_t)env + 0], g_com_vel[3 * (size_t)env + 1], g_com_vel[3 * (size_t)env + 2]};

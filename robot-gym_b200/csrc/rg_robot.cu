@@ -733,6 +733,7 @@ extern "C" int rg_control_step(const void* mpc_ws, const void* robot_ws, int n_e
   RG_REQUIRE(s->desired_leg_state && s->leg_state && s->normalized_phase && s->mpc_contact_state && s->swing_foot_target &&
              s->com_velocity_body && s->contact_forces && s->motor_torques && s->action, "rg_control_step outputs");
   RG_REQUIRE(!s->applied_motor_torques || s->motor_velocities, "rg_control_step torque consumer (motor_velocities)");
+  RG_REQUIRE(((uintptr_t)s->foot_positions_base & 15u) == 0, "rg_control_step foot_positions_base (16-byte alignment)");
   cudaStream_t st = (cudaStream_t)stream;
   step_prologue_kernel<<<grid_for(n_env, 128), 128, 0, st>>>((const RgRobotDev*)robot_ws, n_env, *s);
   rg_count_launch();

@@ -227,7 +227,7 @@ class BatchedMPCController(Controller):
         ("base_orientation_xyzw", "GetTrueBaseOrientation", torch.float32, (4,), 4),
         ("base_rpy", "GetBaseRollPitchYaw", torch.float32, (3,), 4),
         ("base_rpy_rate", "GetBaseRollPitchYawRate", torch.float32, (3,), 4),
-        ("foot_positions_base", "GetFootPositionsInBaseFrame", torch.float32, (12,), 4),
+        ("foot_positions_base", "GetFootPositionsInBaseFrame", torch.float32, (12,), 16),
         ("motor_angles", "GetMotorAngles", torch.float32, (12,), 4),
     )
 

@@ -292,7 +292,7 @@ def mpc_build_solve(ws: MpcWorkspace, com_velocity_body, base_rpy, base_rpy_rate
     args = (ws.ptr, n,
             P(com_velocity_body, torch.float32, (3,)), P(base_rpy, torch.float32, (3,)),
             P(base_rpy_rate, torch.float32, (3,)), P(foot_contact_state, torch.uint8, (4,), align=4),
-            P(foot_positions_base.view(n, 12), torch.float32, (12,)), P(command, torch.float32, (3,)),
+            P(foot_positions_base.view(n, 12), torch.float32, (12,), align=16), P(command, torch.float32, (3,)),
             P(com_height, torch.float32, (), allow_none=True),
             P(contact_forces, torch.float32, (12,)), hf,
             P(solve_info, torch.int32, (4,), allow_none=True))

@@ -32,9 +32,10 @@ def _description_for(robot):
 
 class PyBulletRobotAdapter:
     # (attribute, getter on the stock robot, number of floats)
-    _FLOAT_FIELDS = (("base_velocity_world", "GetBaseVelocity", 3), ("base_orientation_xyzw", "GetTrueBaseOrientation", 4),
-                     ("base_rpy", "GetBaseRollPitchYaw", 3), ("base_rpy_rate", "GetBaseRollPitchYawRate", 3),
-                     ("foot_positions_base", "GetFootPositionsInBaseFrame", 12), ("motor_angles", "GetMotorAngles", 12))
+    # foot positions first: the solve kernel reads them with 128-bit loads (16-byte aligned)
+    _FLOAT_FIELDS = (("foot_positions_base", "GetFootPositionsInBaseFrame", 12), ("motor_angles", "GetMotorAngles", 12),
+                     ("base_orientation_xyzw", "GetTrueBaseOrientation", 4), ("base_velocity_world", "GetBaseVelocity", 3),
+                     ("base_rpy", "GetBaseRollPitchYaw", 3), ("base_rpy_rate", "GetBaseRollPitchYawRate", 3))
 
     def __init__(self, robot, description=None, device="cuda"):
         self._robot = robot
