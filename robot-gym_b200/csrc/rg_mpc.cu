@@ -64,7 +64,14 @@ template <int H>
 struct Cfg {
   static constexpr int N6 = 6 * H;
   static constexpr int NB = 4 * H;
-  static constexpr int NT = ((N6 + 31) / 32) * 32;
+#ifndef RG_RICCATI_MIN_H
+#define RG_RICCATI_MIN_H 20
+#endif
+  // Threads per CTA.  Dense path: one per row of Psi (6h) for the Cholesky.  Riccati path: the sweeps run in one warp,
+  // so only the 4h (step, leg) block threads are needed -- the 6h "rows" of K-products are looped over (h = 20: 96
+  // threads instead of 128, i.e. 5 resident CTAs per SM at 128 registers instead of 4).
+  static constexpr bool RICCATI_ = H >= RG_RICCATI_MIN_H;
+  static constexpr int NT = RICCATI_ ? ((NB + 31) / 32) * 32 : ((N6 + 31) / 32) * 32;
   static constexpr int NW = NT / 32;
   // Psi rows are stored with an even number of slots each (row i holds i+1 entries) so that every row
   // starts 16-byte aligned and the hot loops can use 128-bit shared-memory loads: see prow().
@@ -101,7 +108,7 @@ struct Cfg {
 #define RG_RICCATI_MIN_H 20
 #endif
 #ifndef RG_MIN_BLOCKS_H20
-#define RG_MIN_BLOCKS_H20 4
+#define RG_MIN_BLOCKS_H20 5
 #endif
   static constexpr bool RICCATI = H >= RG_RICCATI_MIN_H;
   // active-set basis of a block in named registers (no local-memory frame: DRAM traffic = algorithmic bytes) or in small
@@ -983,8 +990,8 @@ __device__ __forceinline__ void apply_p(Smem<H>& sm, const RgMpcDev* __restrict_
     for (int c = 0; c < 6; ++c) sm.avec[6 * b.t + c] = a6[c];
   }
   __syncthreads();
-  if (tid < N6) {
-    const int j = tid / 6, c = tid - 6 * j;
+  for (int row = tid; row < N6; row += Cfg<H>::NT) {
+    const int j = row / 6, c = row - 6 * j;
     double s1 = 0.0;
     for (int k = 0; k < H; ++k) s1 = fma(c1f(H, j, k), sm.avec[6 * k + c], s1);
     double val = sm.k1[c] * s1;
@@ -1002,7 +1009,7 @@ __device__ __forceinline__ void apply_p(Smem<H>& sm, const RgMpcDev* __restrict_
       for (int k = 0; k < H; ++k) s2 = fma(ws->c2tab[j * H + k], sm.avec[6 * k + c], s2);
       val += sm.k2lin[c - 3] * s2;
     }
-    sm.kvec[tid] = val;
+    sm.kvec[row] = val;
   }
   __syncthreads();
   if (b.act) {
@@ -1466,11 +1473,11 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
       }
     }
     __syncthreads();
-    if (tid < N6) {
-      const int j = tid / 6, c = tid % 6;
+    for (int row = tid; row < N6; row += C::NT) {
+      const int j = row / 6, c = row % 6;
       double acc = 0.0;
       for (int i = j + 1; i <= H; ++i) acc += 2.0 * (dt * sm.kvec[6 * (i - 1) + c] + dt2 * (i - j - 0.5) * sm.avec[6 * (i - 1) + c]);
-      sm.gt[tid] = acc;
+      sm.gt[row] = acc;
     }
   }
   __syncthreads();
