@@ -879,10 +879,10 @@ __device__ RG_HEAVY_INLINE void riccati_solve(SM& sm) {
 #pragma unroll 1
   for (int t = 0; t < H; ++t) {
     const double* __restrict__ pgt = sm.fac_pg[t];
-    const double bc = sm.avec[6 * t + c6];
+    const double bc = lane < 6 ? sm.avec[6 * t + lane] : 0.0;   // every lane touches only the slots it writes itself
     const double xs = __shfl_down_sync(kFull, x, 6);
     const double zx = lane < 6 ? x + xs : x;              // Phi x = (pi + sigma; sigma)
-    double y0 = sm.rvec[6 * t + c6], y1 = 0.0, y2 = 0.0;
+    double y0 = lane < 6 ? sm.rvec[6 * t + lane] : 0.0, y1 = 0.0, y2 = 0.0;
 #pragma unroll
     for (int k = 0; k < 12; k += 3) {
       y0 = fma(pgt[6 * k + c6], __shfl_sync(kFull, zx, k), y0);

@@ -17,6 +17,8 @@ run_summary(f"{tag}_prof_bench_mpc.ncu-rep", f"{tag}_mpc_ncu_summary",
             f"{note} mpc_solve_kernel<10> inside `python bench.py` (4096 envs, BASELINE config[1]); ncu --set full --clock-control none. "
             "dram_bytes_per_launch feeds bench.py roofline.traffic.")
 run_summary(f"{tag}_prof_mpc_65536.ncu-rep", f"{tag}_mpc_ncu_summary_65536", f"{note} same kernel at 65536 envs (tools/perf_mpc.py): steady state, 55 waves.")
+if os.path.exists(os.path.join(src, f"{tag}_prof_mpc_h20.ncu-rep")):
+    run_summary(f"{tag}_prof_mpc_h20.ncu-rep", f"{tag}_mpc_ncu_summary_h20", f"{note} lean kernel at h = 20 (Riccati sweep), 16384 envs (tools/perf_mpc.py).")
 
 # launch list -> per-kernel shares
 rows = list(csv.reader(open(os.path.join(src, f"{tag}_launches.csv"))))
@@ -30,19 +32,22 @@ for r in rows[hi + 1:]:
     us = v / 1e3 if r[mu] in ("ns", "nsecond") else (v if r[mu] in ("us", "usecond") else v * 1e3)
     a = agg.setdefault(r[kn], [0, 0.0]); a[0] += 1; a[1] += us
 tot = sum(a[1] for a in agg.values())
-own = [k for k in agg if "mpc_solve_kernel" in k or "step_prologue" in k or "step_epilogue" in k]
-step_kernels = {k: v for k, v in agg.items() if "mpc_solve_kernel" in k}
+own = [k for k in agg if "mpc_solve_kernel" in k or "mpc_fallback_kernel" in k or "step_prologue" in k or "step_epilogue" in k]
+step_kernels = {k: v for k, v in agg.items() if "mpc_solve_kernel" in k or "mpc_fallback_kernel" in k}
 with open(os.path.join(dst, f"{tag}_launch_list_summary.md"), "w") as fh:
     fh.write(f"# ncu launch list of `python bench.py --steps 2 --warmup 1` ({tag})\n\n"
              "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` -- cold-cache, serialised launches: compare SHARES, not absolute times.\n"
-             f"Raw CSV: profiles/{tag}_launches.csv.  A timed bench step is ONE launch of `mpc_solve_kernel<10>` (its share of the step is 100 %); "
-             "the other launches below belong to the un-timed parts of bench.py (FMA-peak probes, the 65536-env control-step extras, L2 flush memsets, torch fills).\n\n"
+             f"Raw CSV: profiles/{tag}_launches.csv.  A timed bench step is one launch of the lean `mpc_solve_kernel<10, 1>` plus one of "
+             "`mpc_fallback_kernel<10>` (empty queue on the trot batch: a wave of immediate exits); "
+             "the other launches below belong to the un-timed parts of bench.py (FMA-peak probes, the latency / config-4 / config-5 extras, L2 flush memsets, torch fills).\n\n"
              "| kernel | launches | total us | share of all launches % |\n|---|---|---|---|\n")
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         fh.write(f"| `{k[:110]}` | {c} | {t:.1f} | {100 * t / tot:.1f} |\n")
 shutil.copy(os.path.join(src, f"{tag}_launches.csv"), os.path.join(dst, f"{tag}_launches.csv"))
-for name in ("bench_n1.json", "bench_reference_n1.json", "configs.json", "timeline_4096.log", "pytest_gpu.log"):
-    shutil.copy(os.path.join(src, f"{tag}_{name}"), os.path.join(dst, f"{tag}_{name}"))
+for name in ("bench_n1.json", "bench_reference_n1.json", "configs.json", "timeline_4096.log", "pytest_gpu.log", "config1_substitute.json",
+             "chol_bench.log", "smoke.log"):
+    if os.path.exists(os.path.join(src, f"{tag}_{name}")):
+        shutil.copy(os.path.join(src, f"{tag}_{name}"), os.path.join(dst, f"{tag}_{name}"))
 shutil.copy(os.path.join(src, f"{tag}_racecheck.log"), os.path.join(dst, f"{tag}_compute_sanitizer_racecheck.log"))
 shutil.copy(os.path.join(src, f"{tag}_memcheck.log"), os.path.join(dst, f"{tag}_compute_sanitizer_memcheck.log"))
 print("profiles/ updated:", sorted(f for f in os.listdir(dst) if f.startswith(tag + "_")))
