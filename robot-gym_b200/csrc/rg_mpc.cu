@@ -207,6 +207,12 @@ __device__ __forceinline__ double c1f(int h, int j, int k) { return (double)(h -
 #ifndef RG_COLD_GUESS_LAST
 #define RG_COLD_GUESS_LAST 1
 #endif
+// ... and in the last RG_COLD_GUESS_LAST_4 steps when all four legs stand: the redundant legs are unloaded earlier
+// (fz_min is active at step h-2 on 78 % of the legs of four-stance trot states against 50 % with two stance legs,
+// and a four-stance problem never verifies from the one-step guess alone: tools/experiments/guess_stats.py)
+#ifndef RG_COLD_GUESS_LAST_4
+#define RG_COLD_GUESS_LAST_4 2
+#endif
 // cold start: rounds granted beyond cold_start_rounds while at most this many rows still move
 #ifndef RG_COLD_EXTEND_ROUNDS
 #define RG_COLD_EXTEND_ROUNDS 0
@@ -1742,7 +1748,7 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
       // warm start: the verified active set of this block from the previous solve of the same env
       // (consecutive control steps see almost the same problem); wrong guesses are repaired by the rounds
       act = active_blk ? warm_act : 0u;
-    } else if (RG_COLD_GUESS_LAST && active_blk && t_blk >= H - RG_COLD_GUESS_LAST) {
+    } else if (RG_COLD_GUESS_LAST && active_blk && t_blk >= H - (n_stance == 4 ? RG_COLD_GUESS_LAST_4 : RG_COLD_GUESS_LAST)) {
       // a force in the last step(s) of the horizon barely moves any tracked state, so the regulariser
       // drives it to zero: fz >= fz_min is active there in practically every problem (bit 9)
       act = 1u << 9;

@@ -846,6 +846,139 @@ __device__ __noinline__ void tri_solve_t1(const double* psi, const double* rdiag
   }
 }
 
+// T4: T1's ownership, but the pivot lane's diagonal solve is folded into the update coefficients OFF the dependent
+// chain: every lane loads the pivot block (broadcast), inverts it (RPL x RPL lower triangular) and multiplies its own
+// RPL x RPL block of L with it while the previous step's chain is in flight.  The chain per step is then
+// shuffle(raw x of the pivot lane) -> RPL FMAs, instead of (RPL mul + fma) -> shuffle -> RPL FMAs.
+template <int RPL>
+__device__ __forceinline__ void lower_inverse(const double (*lpp)[RPL], const double* rdp, double (*inv)[RPL]) {
+#pragma unroll
+  for (int c = 0; c < RPL; ++c) {
+    inv[c][c] = rdp[c];
+#pragma unroll
+    for (int cc = c - 1; cc >= 0; --cc) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = cc; k < c; ++k) s = fma(lpp[c][k], inv[k][cc], s);
+      inv[c][cc] = -rdp[c] * s;
+    }
+  }
+}
+
+template <int N6>
+__device__ __noinline__ void tri_solve_t4(const double* psi, const double* rdiag, double* avec) {
+  constexpr int RPL = (N6 + 31) / 32;
+  constexpr int NL = N6 / RPL;
+  static_assert(NL * RPL == N6, "rows must split evenly over the lanes");
+  const int lane = threadIdx.x;
+  const bool active = lane < NL;
+  const int i0 = active ? lane * RPL : 0;
+  double x[RPL];
+  const double* rowp[RPL];
+#pragma unroll
+  for (int r = 0; r < RPL; ++r) { x[r] = active ? avec[i0 + r] : 0.0; rowp[r] = psi + prow(i0 + r); }
+  // ---- forward: L y = b.   coefficients of step p: cf[r][c] = (L[i0+r][pR..] * inv(L_pp))[c]; the pivot lane itself gets inv(L_pp)
+  double cf[RPL][RPL];
+  auto fwd_coef = [&](int p, double (*out)[RPL]) {
+    double lpp[RPL][RPL], rdp[RPL], inv[RPL][RPL], l[RPL][RPL];
+#pragma unroll
+    for (int c = 0; c < RPL; ++c) {
+      rdp[c] = rdiag[p * RPL + c];
+#pragma unroll
+      for (int k = 0; k < c; ++k) lpp[c][k] = psi[prow(p * RPL + c) + p * RPL + k];
+    }
+#pragma unroll
+    for (int r = 0; r < RPL; ++r)
+#pragma unroll
+      for (int c = 0; c < RPL; ++c) l[r][c] = rowp[r][p * RPL + c];   // lanes <= p read past their diagonal: unused
+    lower_inverse<RPL>(lpp, rdp, inv);
+    const bool own = lane == p, later = lane > p;
+#pragma unroll
+    for (int r = 0; r < RPL; ++r)
+#pragma unroll
+      for (int c = 0; c < RPL; ++c) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = c; k < RPL; ++k) s = fma(l[r][k], inv[k][c], s);
+        // later lanes: x_r -= s * xp_c;  pivot lane: x_r = sum_c inv[r][c] xp_c  (written as x_r := 0 + ...);  earlier lanes: untouched
+        out[r][c] = later ? -s : (own ? (c <= r ? inv[r][c] : 0.0) : 0.0);
+      }
+  };
+  fwd_coef(0, cf);
+#pragma unroll 1
+  for (int p = 0; p < NL; ++p) {
+    double cn[RPL][RPL];
+    fwd_coef(p + 1 < NL ? p + 1 : p, cn);
+    double xb[RPL];
+#pragma unroll
+    for (int c = 0; c < RPL; ++c) xb[c] = __shfl_sync(kFull, x[c], p);
+    const bool own = lane == p;
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+      double v = own ? 0.0 : x[r];
+#pragma unroll
+      for (int c = 0; c < RPL; ++c) v = fma(cf[r][c], xb[c], v);
+      x[r] = v;
+    }
+#pragma unroll
+    for (int r = 0; r < RPL; ++r)
+#pragma unroll
+      for (int c = 0; c < RPL; ++c) cf[r][c] = cn[r][c];
+  }
+  // ---- backward: L^T x = y.   x_p = inv(L_pp)^T yhat_p;  earlier lanes: x_r -= sum_c L[pR+c][i0+r] x_p[c] = sum_c' cb[r][c'] yhat_p[c']
+  auto bwd_coef = [&](int p, double (*out)[RPL]) {
+    double lpp[RPL][RPL], rdp[RPL], inv[RPL][RPL], l[RPL][RPL];
+#pragma unroll
+    for (int c = 0; c < RPL; ++c) {
+      rdp[c] = rdiag[p * RPL + c];
+#pragma unroll
+      for (int k = 0; k < c; ++k) lpp[c][k] = psi[prow(p * RPL + c) + p * RPL + k];
+    }
+#pragma unroll
+    for (int c = 0; c < RPL; ++c) {
+      const double* rp = psi + prow(p * RPL + c) + i0;            // row of the pivot, my columns
+#pragma unroll
+      for (int r = 0; r < RPL; ++r) l[c][r] = rp[r];
+    }
+    lower_inverse<RPL>(lpp, rdp, inv);
+    const bool own = lane == p, earlier = lane < p;
+#pragma unroll
+    for (int r = 0; r < RPL; ++r)
+#pragma unroll
+      for (int cc = 0; cc < RPL; ++cc) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c <= cc; ++c) s = fma(l[c][r], inv[cc][c], s);
+        out[r][cc] = earlier ? -s : (own ? (cc >= r ? inv[cc][r] : 0.0) : 0.0);
+      }
+  };
+  bwd_coef(NL - 1, cf);
+#pragma unroll 1
+  for (int p = NL - 1; p >= 0; --p) {
+    double cn[RPL][RPL];
+    bwd_coef(p > 0 ? p - 1 : 0, cn);
+    double xb[RPL];
+#pragma unroll
+    for (int c = 0; c < RPL; ++c) xb[c] = __shfl_sync(kFull, x[c], p);
+    const bool own = lane == p;
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+      double v = own ? 0.0 : x[r];
+#pragma unroll
+      for (int c = 0; c < RPL; ++c) v = fma(cf[r][c], xb[c], v);
+      x[r] = v;
+    }
+#pragma unroll
+    for (int r = 0; r < RPL; ++r)
+#pragma unroll
+      for (int c = 0; c < RPL; ++c) cf[r][c] = cn[r][c];
+  }
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) avec[i0 + r] = x[r];
+  }
+}
+
 template <int N6, int VARIANT>
 __global__ void __launch_bounds__(((N6 + 31) / 32) * 32, 8)
 solve_kernel(const double* __restrict__ a_dense, const double* __restrict__ rhs, double* __restrict__ x_out, long long* __restrict__ cycles, int reps) {
@@ -870,6 +1003,7 @@ solve_kernel(const double* __restrict__ a_dense, const double* __restrict__ rhs,
       if (VARIANT == 1) tri_solve_t1<N6, false>(psi, rdiag, avec);
       if (VARIANT == 2) tri_solve_t1<N6, true>(psi, rdiag, avec);
       if (VARIANT == 3) tri_solve_t3<N6>(psi, rdiag, avec);
+      if (VARIANT == 4) tri_solve_t4<N6>(psi, rdiag, avec);
     }
     __syncthreads();
     total += clock64() - t0;
@@ -924,6 +1058,7 @@ void run_all() {
   double *d_a, *d_l; long long* d_cyc;
   cudaMalloc(&d_a, sizeof(double) * N6 * N6); cudaMalloc(&d_l, sizeof(double) * N6 * N6); cudaMalloc(&d_cyc, 64);
   cudaMemcpy(d_a, a.data(), sizeof(double) * N6 * N6, cudaMemcpyHostToDevice);
+  if (!getenv("SOLVE_ONLY")) {
   run<N6, 0>("v0 current (4-wide, hand pipelined)", d_a, l, d_l, d_cyc);
   run<N6, 1>("panel W=4 unroll 2", d_a, l, d_l, d_cyc);
   run<N6, 2>("panel W=6 unroll 2", d_a, l, d_l, d_cyc);
@@ -935,6 +1070,8 @@ void run_all() {
   run_sq<N6, 0>("square LD=N+2, LDS.128, W=4 u2", d_a, l, d_l, d_cyc);
   run_sq<N6, 1>("square LD=N+2, LDS.128, W=6 u2", d_a, l, d_l, d_cyc);
   run_sq<N6, 2>("square LD=N+2, LDS.128, W=4 u4", d_a, l, d_l, d_cyc);
+  }
+  if (getenv("CHOL_ONLY")) return;
   {
     std::vector<double> b(N6), y(N6), x(N6);
     for (auto& v : b) v = rand() / (double)RAND_MAX - 0.5;
@@ -946,6 +1083,7 @@ void run_all() {
     run_solve<N6, 1>("t1 consecutive rows, lane blocks", d_a, d_b, x, d_x, d_cyc);
     run_solve<N6, 2>("t1 + prefetch (forward)", d_a, d_b, x, d_x, d_cyc);
     run_solve<N6, 3>("t3 = t0 + own rdiag in registers", d_a, d_b, x, d_x, d_cyc);
+    run_solve<N6, 4>("t4 = t1, pivot solve folded into coefs", d_a, d_b, x, d_x, d_cyc);
     cudaFree(d_b); cudaFree(d_x);
   }
   cudaFree(d_a); cudaFree(d_l); cudaFree(d_cyc);
