@@ -484,12 +484,16 @@ __device__ RG_HEAVY_INLINE void cholesky_rows_w(SM& sm, int j_begin) {
   }
 }
 
-// ---- Psi x = b with the factor, b/x in sm.avec; executed by warp 0 only ----------------------
+// ---- Psi x = b with the factor, b/x in sm.avec; executed by one warp ---------------------------
 // Each lane owns RPL CONSECUTIVE rows (30 lanes x 1, 2 or 4 rows).  One step eliminates the RPL pivots
 // of one lane: a lane-local RPL x RPL triangular solve with the own diagonal reciprocals held in
-// registers, RPL shuffles in flight together, then RPL FMAs per owned row -- all predicated, no
-// divergent branch and no shared-memory load on the pivot chain.  (tools/microbench/chol_bench.cu:
-// 8.7-9.3k cycles per solve alone on an SM against 14.8k for one-pivot-per-step with strided rows.)
+// registers, RPL shuffles in flight together, then RPL FMAs per owned row.  A single warp issues an
+// instruction every ~4 cycles, so the sweep's time is its instruction count: the updates are predicated
+// FMAs with negated operands (no negate / select pairs), the pivot lane is not patched per step (its rows
+// stop changing at its own step: every lane solves its own diagonal block ONCE after the sweep), and the
+// pivot rows of the backward sweep are addressed by additions.  27 / 30 instructions per step instead of
+// 40 / 45 (tools/microbench/chol_bench.cu t5: 6.2k cycles per solve alone on an SM against 9.3k, 11.1k
+// against 14.0k with 8 CTAs per SM; one pivot per step with strided rows: 14.8k).
 // T(i) mod 16 is a permutation over the even and over the odd rows of 16 consecutive lanes, so the
 // per-column loads stay bank-conflict free with this ownership too.
 template <int H, class SM>
@@ -501,7 +505,7 @@ __device__ RG_HEAVY_INLINE void tri_solve_warp0(SM& sm) {
   const int lane = threadIdx.x & 31;   // one warp runs this routine (sm.solver_warp)
   const bool active = lane < NL;
   const int i0 = active ? lane * RPL : 0;
-  double x[RPL], rd[RPL], lb[RPL][RPL], l[RPL][RPL];
+  double x[RPL], rd[RPL], lb[RPL][RPL];
   const double* rowp[RPL];
 #pragma unroll
   for (int r = 0; r < RPL; ++r) {
@@ -513,7 +517,8 @@ __device__ RG_HEAVY_INLINE void tri_solve_warp0(SM& sm) {
   }
   // forward: L y = b
 #pragma unroll 1
-  for (int p = 0; p < NL; ++p) {
+  for (int p = 0; p < NL - 1; ++p) {
+    double l[RPL][RPL];
 #pragma unroll
     for (int r = 0; r < RPL; ++r)
 #pragma unroll
@@ -528,22 +533,35 @@ __device__ RG_HEAVY_INLINE void tri_solve_warp0(SM& sm) {
     }
 #pragma unroll
     for (int c = 0; c < RPL; ++c) yb[c] = __shfl_sync(kFull, y[c], p);
-    const bool own = lane == p, later = lane > p;
+    if (lane > p) {
 #pragma unroll
-    for (int c = 0; c < RPL; ++c)
+      for (int c = 0; c < RPL; ++c)
 #pragma unroll
-      for (int r = 0; r < RPL; ++r) x[r] = fma(later ? -l[r][c] : 0.0, yb[c], x[r]);
+        for (int r = 0; r < RPL; ++r) x[r] = fma(-l[r][c], yb[c], x[r]);
+    }
+  }
+  // every lane: y of its own rows (x has been final since the lane's own pivot step)
 #pragma unroll
-    for (int c = 0; c < RPL; ++c) x[c] = own ? y[c] : x[c];
+  for (int c = 0; c < RPL; ++c) {
+    double v = x[c];
+#pragma unroll
+    for (int cc = 0; cc < c; ++cc) v = fma(-lb[c][cc], x[cc], v);
+    x[c] = v * rd[c];
   }
   // backward: L^T x = y
+  const double* rp = sm.psi + prow((NL - 1) * RPL) + i0;        // first row of the pivot lane, my columns
+  int rlen = (NL - 1) * RPL;                                     // prow(i) - prow(i - 1) = i
 #pragma unroll 1
-  for (int p = NL - 1; p >= 0; --p) {
+  for (int p = NL - 1; p > 0; --p) {
+    double l[RPL][RPL];
+    {
+      const double* q = rp;
 #pragma unroll
-    for (int c = 0; c < RPL; ++c) {
-      const double* rp = sm.psi + prow(p * RPL + c) + i0;           // row of the pivot, my columns
+      for (int c = 0; c < RPL; ++c) {
 #pragma unroll
-      for (int r = 0; r < RPL; ++r) l[c][r] = rp[r];
+        for (int r = 0; r < RPL; ++r) l[c][r] = q[r];
+        q += rlen + c + 1;                                        // next row of the packed triangle
+      }
     }
     double z[RPL], zb[RPL];
 #pragma unroll
@@ -555,13 +573,22 @@ __device__ RG_HEAVY_INLINE void tri_solve_warp0(SM& sm) {
     }
 #pragma unroll
     for (int c = 0; c < RPL; ++c) zb[c] = __shfl_sync(kFull, z[c], p);
-    const bool own = lane == p, earlier = lane < p;
+    if (lane < p) {
 #pragma unroll
-    for (int c = RPL - 1; c >= 0; --c)
+      for (int c = RPL - 1; c >= 0; --c)
 #pragma unroll
-      for (int r = 0; r < RPL; ++r) x[r] = fma(earlier ? -l[c][r] : 0.0, zb[c], x[r]);
+        for (int r = 0; r < RPL; ++r) x[r] = fma(-l[c][r], zb[c], x[r]);
+    }
+    // step back RPL rows: prow(i - 1) = prow(i) - i
 #pragma unroll
-    for (int c = 0; c < RPL; ++c) x[c] = own ? z[c] : x[c];
+    for (int k = 0; k < RPL; ++k) { rp -= rlen; --rlen; }
+  }
+#pragma unroll
+  for (int c = RPL - 1; c >= 0; --c) {
+    double v = x[c];
+#pragma unroll
+    for (int cc = c + 1; cc < RPL; ++cc) v = fma(-lb[cc][c], x[cc], v);
+    x[c] = v * rd[c];
   }
   if (active) {
 #pragma unroll

@@ -979,6 +979,108 @@ __device__ __noinline__ void tri_solve_t4(const double* psi, const double* rdiag
   }
 }
 
+// T5: T1 with the instruction count per step cut down: predicated FMAs with negated operands instead of
+// negate + select + FMA, no per-step fix-up of the pivot lane (every lane finishes with ONE local solve of its
+// own rows after the sweep: its x stops changing at its own pivot step), row pointers advanced by additions.
+template <int N6>
+__device__ __noinline__ void tri_solve_t5(const double* psi, const double* rdiag, double* avec) {
+  constexpr int RPL = (N6 + 31) / 32;
+  constexpr int NL = N6 / RPL;
+  static_assert(NL * RPL == N6, "rows must split evenly over the lanes");
+  const int lane = threadIdx.x;
+  const bool active = lane < NL;
+  const int i0 = active ? lane * RPL : 0;
+  double x[RPL], rd[RPL], lb[RPL][RPL];
+  const double* rowp[RPL];
+#pragma unroll
+  for (int r = 0; r < RPL; ++r) {
+    x[r] = active ? avec[i0 + r] : 0.0;
+    rd[r] = rdiag[i0 + r];
+    rowp[r] = psi + prow(i0 + r);
+#pragma unroll
+    for (int c = 0; c < r; ++c) lb[r][c] = rowp[r][i0 + c];
+  }
+  // ---- forward: L y = b
+#pragma unroll 1
+  for (int p = 0; p < NL - 1; ++p) {
+    double l[RPL][RPL];
+#pragma unroll
+    for (int r = 0; r < RPL; ++r)
+#pragma unroll
+      for (int c = 0; c < RPL; ++c) l[r][c] = rowp[r][p * RPL + c];   // lanes <= p read past their diagonal: value unused
+    double y[RPL], yb[RPL];
+#pragma unroll
+    for (int c = 0; c < RPL; ++c) {
+      double v = x[c];
+#pragma unroll
+      for (int cc = 0; cc < c; ++cc) v = fma(-lb[c][cc], y[cc], v);
+      y[c] = v * rd[c];
+    }
+#pragma unroll
+    for (int c = 0; c < RPL; ++c) yb[c] = __shfl_sync(kFull, y[c], p);
+    if (lane > p) {
+#pragma unroll
+      for (int c = 0; c < RPL; ++c)
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) x[r] = fma(-l[r][c], yb[c], x[r]);
+    }
+  }
+  // every lane: y of its own rows (its x is final since its own pivot step)
+#pragma unroll
+  for (int c = 0; c < RPL; ++c) {
+    double v = x[c];
+#pragma unroll
+    for (int cc = 0; cc < c; ++cc) v = fma(-lb[c][cc], x[cc], v);
+    x[c] = v * rd[c];
+  }
+  // ---- backward: L^T x = y
+  const double* rp = psi + prow((NL - 1) * RPL) + i0;          // row of the pivot (first of the lane's rows), my columns
+  int rlen = (NL - 1) * RPL;                                    // prow(i) - prow(i - 1) = i
+#pragma unroll 1
+  for (int p = NL - 1; p > 0; --p) {
+    double l[RPL][RPL];
+    {
+      const double* q = rp;
+#pragma unroll
+      for (int c = 0; c < RPL; ++c) {
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) l[c][r] = q[r];
+        q += rlen + c + 1;                                       // next row of the packed triangle
+      }
+    }
+    double z[RPL], zb[RPL];
+#pragma unroll
+    for (int c = RPL - 1; c >= 0; --c) {
+      double v = x[c];
+#pragma unroll
+      for (int cc = c + 1; cc < RPL; ++cc) v = fma(-lb[cc][c], z[cc], v);
+      z[c] = v * rd[c];
+    }
+#pragma unroll
+    for (int c = 0; c < RPL; ++c) zb[c] = __shfl_sync(kFull, z[c], p);
+    if (lane < p) {
+#pragma unroll
+      for (int c = RPL - 1; c >= 0; --c)
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) x[r] = fma(-l[c][r], zb[c], x[r]);
+    }
+    // step back RPL rows: prow(i - RPL) = prow(i) - sum_{k=0}^{RPL-1} (i - k)
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) { rp -= rlen; --rlen; }
+  }
+#pragma unroll
+  for (int c = RPL - 1; c >= 0; --c) {
+    double v = x[c];
+#pragma unroll
+    for (int cc = c + 1; cc < RPL; ++cc) v = fma(-lb[cc][c], x[cc], v);
+    x[c] = v * rd[c];
+  }
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) avec[i0 + r] = x[r];
+  }
+}
+
 template <int N6, int VARIANT>
 __global__ void __launch_bounds__(((N6 + 31) / 32) * 32, 8)
 solve_kernel(const double* __restrict__ a_dense, const double* __restrict__ rhs, double* __restrict__ x_out, long long* __restrict__ cycles, int reps) {
@@ -1004,6 +1106,7 @@ solve_kernel(const double* __restrict__ a_dense, const double* __restrict__ rhs,
       if (VARIANT == 2) tri_solve_t1<N6, true>(psi, rdiag, avec);
       if (VARIANT == 3) tri_solve_t3<N6>(psi, rdiag, avec);
       if (VARIANT == 4) tri_solve_t4<N6>(psi, rdiag, avec);
+      if (VARIANT == 5) tri_solve_t5<N6>(psi, rdiag, avec);
     }
     __syncthreads();
     total += clock64() - t0;
@@ -1084,6 +1187,7 @@ void run_all() {
     run_solve<N6, 2>("t1 + prefetch (forward)", d_a, d_b, x, d_x, d_cyc);
     run_solve<N6, 3>("t3 = t0 + own rdiag in registers", d_a, d_b, x, d_x, d_cyc);
     run_solve<N6, 4>("t4 = t1, pivot solve folded into coefs", d_a, d_b, x, d_x, d_cyc);
+    run_solve<N6, 5>("t5 = t1, predicated, no own fix-up", d_a, d_b, x, d_x, d_cyc);
     cudaFree(d_b); cudaFree(d_x);
   }
   cudaFree(d_a); cudaFree(d_l); cudaFree(d_cyc);
