@@ -203,6 +203,10 @@ __device__ __forceinline__ double c1f(int h, int j, int k) { return (double)(h -
 #ifndef RG_CHOL_LDS128
 #define RG_CHOL_LDS128 1
 #endif
+// unroll factor of that loop (2 or 4): a trip moves five pointers and rotates the lagged operands, ~10 of 38 instructions at 2
+#ifndef RG_CHOL_UNROLL
+#define RG_CHOL_UNROLL 4
+#endif
 // cold start: fz >= fz_min is guessed active in the last RG_COLD_GUESS_LAST steps of the horizon (0 = empty set)
 #ifndef RG_COLD_GUESS_LAST
 #define RG_COLD_GUESS_LAST 1
@@ -250,6 +254,20 @@ __device__ __forceinline__ double quad_sum(double v) {   // sum over the 4 legs 
   v += __shfl_xor_sync(kFull, v, 1);
   v += __shfl_xor_sync(kFull, v, 2);
   return v;
+}
+
+// 1 / sqrt(d) for the Cholesky pivots: hardware seed (MUFU.RSQ64H, ~2^-21 relative) and one third-order step
+// y (1 + e/2 + 3 e^2/8), e = 1 - d y^2  (error 5 e^3 / 16 < 2^-60): 6 instructions on the pivot chain instead of the 12
+// of rsqrt() with its range checks.  No special cases: d <= 0 gives NaN / inf, which the caller tests for once per panel.
+__device__ __forceinline__ double rsqrt_pivot(double d) {
+#ifdef RG_LIBM_RSQRT
+  return rsqrt(d);
+#else
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double e = fma(-(d * y), y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
+#endif
 }
 
 // ---- in-place Cholesky of the packed SPD matrix: one thread per row, panels of 4 columns --------
@@ -300,7 +318,11 @@ __device__ RG_HEAVY_INLINE void cholesky_rows(SM& sm, int j_begin) {
         double2 b0 = ld2v(p0), b3 = ld2v(p3);
         double b1x = p1[0], b2x = p2[0];
         double2 q1 = ld2v(p1 + 1), q2 = ld2v(p2 + 1);
+#if RG_CHOL_UNROLL == 4
+#pragma unroll 4
+#else
 #pragma unroll 2
+#endif
         for (int g = 0; g < ng; ++g) {
           const double2 an = ld2(r2 + 2 * g + 2);
           const double2 c0 = ld2v(p0 + 2 * g + 2), c3 = ld2v(p3 + 2 * g + 2);
@@ -352,16 +374,15 @@ __device__ RG_HEAVY_INLINE void cholesky_rows(SM& sm, int j_begin) {
 #pragma unroll
           for (int c = 0; c <= r; ++c) if (r >= w) a[r][c] = (r == c ? 1.0 : 0.0);
       }
-      // factor: l[r][c] for c < r, inverse diagonal in rd[r]
+      // factor: l[r][c] for c < r, inverse diagonal in rd[r].  A non-positive pivot turns rd[] into NaN / inf (no clamp on
+      // the chain): one test of the product catches it, the caller gives the factorisation up (sm.flag).
       double rd[4];
-      bool bad = false;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         double d = a[c][c];
 #pragma unroll
         for (int k = 0; k < c; ++k) d = fma(-a[c][k], a[c][k], d);
-        if (!(d > 0.0)) { bad = true; d = 1e-300; }
-        rd[c] = rsqrt(d);
+        rd[c] = rsqrt_pivot(d);
 #pragma unroll
         for (int r = c + 1; r < 4; ++r) {
           double v = a[r][c];
@@ -370,30 +391,22 @@ __device__ RG_HEAVY_INLINE void cholesky_rows(SM& sm, int j_begin) {
           a[r][c] = v * rd[c];
         }
       }
+      // x L_JJ^T = acc: forward substitution over the panel columns.  A panel row runs the same code: its acc[] are the
+      // block entries A'[r][0..r], so x[c] = L[r][c] for c < r -- only the entries strictly left of the diagonal are stored.
+      double x[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        double v = acc[c];
+#pragma unroll
+        for (int k = 0; k < c; ++k) v = fma(-x[k], a[c][k], v);
+        x[c] = v * rd[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) if (c < w && j0 + c < i) row_i[j0 + c] = x[c];
       if (i < j0 + w) {
-        // panel row r = i - j0: its factored entries are a[r][0..r-1], diagonal -> rdiag
         const int r = i - j0;
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-          if (rr == r) {
-#pragma unroll
-            for (int c = 0; c < rr; ++c) row_i[j0 + c] = a[rr][c];
-            sm.rdiag[i] = rd[rr];
-          }
-        }
-        if (bad && r == 0) sm.flag = 1;
-      } else {
-        // x L_JJ^T = acc  ->  forward substitution over the panel columns
-        double x[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          double v = acc[c];
-#pragma unroll
-          for (int k = 0; k < c; ++k) v = fma(-x[k], a[c][k], v);
-          x[c] = v * rd[c];
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) if (c < w) row_i[j0 + c] = x[c];
+        sm.rdiag[i] = r == 0 ? rd[0] : (r == 1 ? rd[1] : (r == 2 ? rd[2] : rd[3]));
+        if (r == 0 && !((rd[0] * rd[1]) * (rd[2] * rd[3]) < 1e300)) sm.flag = 1;
       }
     }
     RG_TOCL(31, N6 - 1);
