@@ -1361,10 +1361,16 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
 
   RG_TIC();
   const double roll = in_roll, pitch = in_pitch, yaw = zero_yaw ? 0.0 : (double)in_yaw;
-  double sr, cr, sp, cp, sy, cy;
-  sincos(roll, &sr, &cr);
-  sincos(pitch, &sp, &cp);
-  sincos(yaw, &sy, &cy);
+  // Everything derived from the attitude (trigonometry, T(rpy), lever arms, I_w^-1) is consumed by threads of warp 0
+  // only (tid < 9 / 4 / H): the other warps skip the computation -- a warp pays for an instruction whether one lane
+  // needs the result or all of them.
+  const bool setup_warp = tid < 32;
+  double sr = 0.0, cr = 1.0, sp = 0.0, cp = 1.0, sy = 0.0, cy = 1.0;
+  if (setup_warp) {
+    sincos(roll, &sr, &cr);
+    sincos(pitch, &sp, &cp);
+    sincos(yaw, &sy, &cy);
+  }
 
   // ---------------------------------------------------------------- setup (thread 0..; tiny)
   if (tid == 0) {
@@ -1384,7 +1390,11 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
 
   RG_TOC(40);
   // T(rpy): angular velocity -> rpy rate;  K2_ang = 2 dt^4 T^T diag(w_rpy) T
-  const double tm[9] = {cy / cp, sy / cp, 0.0, -sy, cy, 0.0, cy * sp / cp, sy * sp / cp, 1.0};
+  double tm[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0};
+  if (setup_warp) {
+    const double icp = 1.0 / cp;
+    tm[0] = cy * icp; tm[1] = sy * icp; tm[3] = -sy; tm[4] = cy; tm[6] = cy * sp * icp; tm[7] = sy * sp * icp;
+  }
   const double dt2 = dt * dt, dt4 = dt2 * dt2;
   if (tid < 9) {
     const int c = tid / 3, d = tid % 3;
@@ -1398,8 +1408,8 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
 
   // foot lever arms in the (yaw aligned) world frame: R = Rx Ry Rz (sic, see oracle/convex_mpc.py)
   // R_body = Rz Ry Rx for the inertia
-  double com_z;
-  {
+  double com_z = 0.0;
+  if (setup_warp) {
     const double rf[9] = {cp * cy, -cp * sy, sp,
                           sr * sp * cy + cr * sy, -sr * sp * sy + cr * cy, -sr * cp,
                           -cr * sp * cy + sr * sy, cr * sp * sy + sr * cy, cr * cp};
