@@ -1235,27 +1235,30 @@ __device__ __forceinline__ void build_basis(unsigned& act, bool active_blk, cons
   B.bt0 = B.bt1 = B.bt2 = 0.0;
   B.row0 = B.row1 = B.row2 = -1;
   B.na = 0;
-  if (!active_blk) return;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    if (((act >> r) & 1u) && B.na < 3) {
-      const int rw = r < 5 ? r : r - 5;                                  // compile-time: the loop is unrolled
-      double a0 = rw == 0 ? -1.0 : (rw == 1 ? 1.0 : 0.0), a1 = rw == 2 ? -1.0 : (rw == 3 ? 1.0 : 0.0), a2 = rw < 4 ? mu[rw] : 1.0;
-      const double target = r < 5 ? hv_up[rw] : lo_b[rw];
-      const double c0 = B.na > 0 ? a0 * B.e0[0] + a1 * B.e0[1] + a2 * B.e0[2] : 0.0;
-      a0 -= c0 * B.e0[0]; a1 -= c0 * B.e0[1]; a2 -= c0 * B.e0[2];
-      const double c1 = B.na > 1 ? a0 * B.e1[0] + a1 * B.e1[1] + a2 * B.e1[2] : 0.0;
-      a0 -= c1 * B.e1[0]; a1 -= c1 * B.e1[1]; a2 -= c1 * B.e1[2];
-      const double nrm = sqrt(a0 * a0 + a1 * a1 + a2 * a2);
-      if (nrm < 1e-9) {
-        act &= ~(1u << r);                                               // dependent normal: drop
-      } else {
-        const double inrm = 1.0 / nrm;
-        if (B.na == 0) { B.e0[0] = a0 * inrm; B.e0[1] = a1 * inrm; B.e0[2] = a2 * inrm; B.r00 = nrm; B.bt0 = target; B.row0 = r; }
-        else if (B.na == 1) { B.e1[0] = a0 * inrm; B.e1[1] = a1 * inrm; B.e1[2] = a2 * inrm; B.r01 = c0; B.r11 = nrm; B.bt1 = target; B.row1 = r; }
-        else { B.e2[0] = a0 * inrm; B.e2[1] = a1 * inrm; B.e2[2] = a2 * inrm; B.r02 = c0; B.r12 = c1; B.r22 = nrm; B.bt2 = target; B.row2 = r; }
-        ++B.na;
-      }
+  // One Gram-Schmidt body, run once per set bit (in bit order) until three independent rows are held: an unrolled scan
+  // of the ten rows was 1300 instructions of code for the same handful of executed steps.
+  unsigned bits = active_blk ? (act & 0x3ffu) : 0u;
+#pragma unroll 1
+  while (bits != 0u && B.na < 3) {
+    const int r = __ffs((int)bits) - 1;
+    bits &= bits - 1u;
+    const int rw = r < 5 ? r : r - 5;
+    double a0 = rw == 0 ? -1.0 : (rw == 1 ? 1.0 : 0.0), a1 = rw == 2 ? -1.0 : (rw == 3 ? 1.0 : 0.0);
+    double a2 = rw == 0 ? mu[0] : (rw == 1 ? mu[1] : (rw == 2 ? mu[2] : (rw == 3 ? mu[3] : 1.0)));
+    const double target = r < 5 ? (rw < 4 ? hv_up[0] : hv_up[4]) : (rw < 4 ? lo_b[0] : lo_b[4]);   // the four cone rows share their bounds
+    const double c0 = B.na > 0 ? a0 * B.e0[0] + a1 * B.e0[1] + a2 * B.e0[2] : 0.0;
+    a0 -= c0 * B.e0[0]; a1 -= c0 * B.e0[1]; a2 -= c0 * B.e0[2];
+    const double c1 = B.na > 1 ? a0 * B.e1[0] + a1 * B.e1[1] + a2 * B.e1[2] : 0.0;
+    a0 -= c1 * B.e1[0]; a1 -= c1 * B.e1[1]; a2 -= c1 * B.e1[2];
+    const double n2 = a0 * a0 + a1 * a1 + a2 * a2;
+    if (n2 < 1e-18) {
+      act &= ~(1u << r);                                               // dependent normal: drop
+    } else {
+      const double inrm = rsqrt_pivot(n2), nrm = n2 * inrm;
+      if (B.na == 0) { B.e0[0] = a0 * inrm; B.e0[1] = a1 * inrm; B.e0[2] = a2 * inrm; B.r00 = nrm; B.bt0 = target; B.row0 = r; }
+      else if (B.na == 1) { B.e1[0] = a0 * inrm; B.e1[1] = a1 * inrm; B.e1[2] = a2 * inrm; B.r01 = c0; B.r11 = nrm; B.bt1 = target; B.row1 = r; }
+      else { B.e2[0] = a0 * inrm; B.e2[1] = a1 * inrm; B.e2[2] = a2 * inrm; B.r02 = c0; B.r12 = c1; B.r22 = nrm; B.bt2 = target; B.row2 = r; }
+      ++B.na;
     }
   }
   // rows beyond the third independent one cannot be held: drop them from the guess
@@ -1367,9 +1370,12 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
   const bool setup_warp = tid < 32;
   double sr = 0.0, cr = 1.0, sp = 0.0, cp = 1.0, sy = 0.0, cy = 1.0;
   if (setup_warp) {
-    sincos(roll, &sr, &cr);
-    sincos(pitch, &sp, &cp);
-    sincos(yaw, &sy, &cy);
+    // one sincos call: lanes 0 / 1 / 2 take roll / pitch / yaw, the six results are broadcast
+    double sn, cs;
+    sincos(tid == 0 ? roll : (tid == 1 ? pitch : yaw), &sn, &cs);
+    sr = __shfl_sync(kFull, sn, 0); cr = __shfl_sync(kFull, cs, 0);
+    sp = __shfl_sync(kFull, sn, 1); cp = __shfl_sync(kFull, cs, 1);
+    sy = __shfl_sync(kFull, sn, 2); cy = __shfl_sync(kFull, cs, 2);
   }
 
   // ---------------------------------------------------------------- setup (thread 0..; tiny)
