@@ -118,6 +118,12 @@ struct Cfg {
 #define RG_BASIS_IN_REGS_H10 1
 #endif
   static constexpr bool BASIS_IN_REGS = (H == 10) && RG_BASIS_IN_REGS_H10;
+  // the gradient at the particular solution is evaluated as "pass -1" of the solve / refine loop (one inlined copy of
+  // apply_p instead of two: less code on the round's path; +1.5 % at h = 10, -3 % at h = 5 where the kernel spills)
+#ifndef RG_GRAD_IN_PASS_LOOP_H10
+#define RG_GRAD_IN_PASS_LOOP_H10 1
+#endif
+  static constexpr bool GRAD_IN_PASS_LOOP = (H == 10) && RG_GRAD_IN_PASS_LOOP_H10;
   static constexpr int CHOL_W = (H == 10) ? RG_CHOL_W_H10 : 4;
   static constexpr int MIN_BLOCKS = H <= 5 ? RG_MIN_BLOCKS_H5 : (H <= 10 ? RG_MIN_BLOCKS_H10 : (RICCATI ? RG_MIN_BLOCKS_H20 : 2));
 };
@@ -227,27 +233,41 @@ __device__ __forceinline__ double c1f(int h, int j, int k) { return (double)(h -
 #ifndef RG_IPM_WARM
 #define RG_IPM_WARM 0.99
 #endif
+#ifndef RG_REBUILD_BASIS
+#define RG_REBUILD_BASIS 1
+#endif
 #ifndef RG_SKIP_REFINE_TOL
 #define RG_SKIP_REFINE_TOL 1e-10
 #endif
 
 // ---- block-wide reductions (all threads call; result valid in all threads) -------------------
-template <int NW>
+// WHAT: bit 0 = the sum, bit 1 = the maximum, bit 2 = the minimum is wanted (the others are left untouched)
+template <int NW, int WHAT = 7>
 __device__ __forceinline__ void block_reduce(double& sum, double& mx, double& mn, double (*red)[8]) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    sum += __shfl_xor_sync(kFull, sum, o);
-    mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));
-    mn = fmin(mn, __shfl_xor_sync(kFull, mn, o));
+    if (WHAT & 1) sum += __shfl_xor_sync(kFull, sum, o);
+    if (WHAT & 2) mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));
+    if (WHAT & 4) mn = fmin(mn, __shfl_xor_sync(kFull, mn, o));
   }
   if (NW == 1) return;
   const int w = threadIdx.x >> 5;
   __syncthreads();   // protect red[] from the previous use
-  if ((threadIdx.x & 31) == 0) { red[0][w] = sum; red[1][w] = mx; red[2][w] = mn; }
+  if ((threadIdx.x & 31) == 0) {
+    if (WHAT & 1) red[0][w] = sum;
+    if (WHAT & 2) red[1][w] = mx;
+    if (WHAT & 4) red[2][w] = mn;
+  }
   __syncthreads();
-  sum = red[0][0]; mx = red[1][0]; mn = red[2][0];
+  if (WHAT & 1) sum = red[0][0];
+  if (WHAT & 2) mx = red[1][0];
+  if (WHAT & 4) mn = red[2][0];
 #pragma unroll
-  for (int i = 1; i < NW; ++i) { sum += red[0][i]; mx = fmax(mx, red[1][i]); mn = fmin(mn, red[2][i]); }
+  for (int i = 1; i < NW; ++i) {
+    if (WHAT & 1) sum += red[0][i];
+    if (WHAT & 2) mx = fmax(mx, red[1][i]);
+    if (WHAT & 4) mn = fmin(mn, red[2][i]);
+  }
 }
 
 __device__ __forceinline__ double quad_sum(double v) {   // sum over the 4 legs of a time step
@@ -1580,7 +1600,7 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
   double qmax = active_blk ? fmax(fabs(q[0]), fmax(fabs(q[1]), fabs(q[2]))) : 0.0;
   {
     double dsum = 0.0, dmn = 0.0;
-    block_reduce<C::NW>(dsum, qmax, dmn, sm.red);
+    block_reduce<C::NW, 2>(dsum, qmax, dmn, sm.red);
   }
   const double qscale = fmax(1.0, qmax);
   if constexpr (!LEAN) {
@@ -1640,7 +1660,7 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
 #pragma unroll
         for (int d = 0; d < 3; ++d) rd0 = fmax(rd0, fabs(pu0[d] + q[d]));
       }
-      block_reduce<C::NW>(dsum, rd0, dmn, sm.red);
+      block_reduce<C::NW, 2>(dsum, rd0, dmn, sm.red);
       const double mu0 = RG_IPM_LAM0 * fmax(qscale, RG_IPM_RD_SCALE * rd0);
 #pragma unroll
       for (int r = 0; r < 10; ++r) lam[r] = active_blk ? mu0 / s[r] : 1.0;
@@ -1665,7 +1685,7 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
         sl += slr;
       }
       if (!active_blk) { sl = 0.0; rdmax = 0.0; }
-      block_reduce<C::NW>(sl, rdmax, dmn, sm.red);
+      block_reduce<C::NW, 3>(sl, rdmax, dmn, sm.red);
       const double mu_c = sl / m_total;
       const double res = fmax(rdmax, mu_c) / qscale;
       RG_TRACE(4 * trace_n + 0, res); RG_TRACE(4 * trace_n + 1, mu_c); RG_TRACE(4 * trace_n + 2, (double)iters); RG_TRACE(4 * trace_n + 3, tol);
@@ -1738,7 +1758,7 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
             xr[r] = (r < 5 ? -c5[r] : c5[r - 5]) * (lam[r] * isl[r]);
             if (active_blk) tmax = fmax(tmax, fmax(-xr[r], 1.0 + xr[r]));
           }
-          block_reduce<C::NW>(dsum, tmax, dmn2, sm.red);
+          block_reduce<C::NW, 2>(dsum, tmax, dmn2, sm.red);
           const double amax = 1.0 / tmax;
           double mu_aff = 0.0;
 #pragma unroll
@@ -1749,7 +1769,7 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
           }
           if (!active_blk) mu_aff = 0.0;
           double dmx3 = 0.0, dmn3 = 0.0;
-          block_reduce<C::NW>(mu_aff, dmx3, dmn3, sm.red);
+          block_reduce<C::NW, 1>(mu_aff, dmx3, dmn3, sm.red);
           mu_aff /= m_total;
           const double ratio = mu_aff / mu_c;
           sigmu = ratio * ratio * ratio * mu_c;
@@ -1765,7 +1785,7 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
         yr[r] = (r < 5 ? -c5[r] : c5[r - 5]) * (lam[r] * isl[r]);
         if (active_blk) tmax = fmax(tmax, fmax(-yr[r], wv[r] * (s[r] * isl[r]) + yr[r]));
       }
-      block_reduce<C::NW>(dsum, tmax, dmn2, sm.red);
+      block_reduce<C::NW, 2>(dsum, tmax, dmn2, sm.red);
       // fraction to the boundary: 0.99 throughout.  (0.999 once the residuals are small saved nothing measurable
       // and made two bound-gait problems in 1.5 M oscillate at mu ~ 1e-4; steps closer to 1 collapse the slacks
       // while the dual residual is still finite and de-centre the iterate.)
@@ -1824,11 +1844,16 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
       // by the run-time row count (fewer live registers across the heavy phases, but a 480-byte frame per thread).
       int na;
       double u0[3], mproj[6];
+#if !RG_REBUILD_BASIS
       BlockBasis B;                                                        // register scheme
+#endif
       double e[3][3], rr[3][3];                                            // array scheme: a_i = sum_k rr[k][i] e_k
       int rows[3] = {-1, -1, -1};
       if constexpr (C::BASIS_IN_REGS) {
         {
+#if RG_REBUILD_BASIS
+          BlockBasis B;
+#endif
           build_basis(act, active_blk, mu, hv_up, lo_b, B);
           na = B.na;
           // particular solution u0 = sum_k c_k e_k with a_i . u0 = b_i  (forward substitution with rr^T; unused slots have
@@ -1913,60 +1938,63 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
       // Only the time steps from the first block whose active set moved since the last factorisation
       // change Psi, and a left-looking Cholesky keeps its leading columns: refactor the tail only
       // (active rows cluster at the end of the horizon: DESIGN.md 3.3).
+      int t_fac;                                                          // first time block to refactorise, -1: none
       {
         double dsum = 0.0, dmx = 0.0, tmin = (double)H;
         if (active_blk && act != act_fact) tmin = (double)t_blk;
         if (!fact_valid) tmin = 0.0;
-        block_reduce<C::NW>(dsum, dmx, tmin, sm.red);
-        if (tmin < (double)H) factor_psi<H>(sm, ws, blk, mproj, C::RICCATI ? 0 : (C::CHOL_W == 4 ? (((int)tmin) & ~1) : (int)tmin));
-        else if (tid == 0) sm.flag = 0;
-        act_fact = act;
-        fact_valid = true;
-        __syncthreads();
+        block_reduce<C::NW, 4>(dsum, dmx, tmin, sm.red);
+        t_fac = tmin < (double)H ? (C::RICCATI ? 0 : (C::CHOL_W == 4 ? (((int)tmin) & ~1) : (int)tmin)) : -1;
       }
       RG_TIC();
+      if (t_fac >= 0) factor_psi<H>(sm, ws, blk, mproj, t_fac);
+      else if (tid == 0) sm.flag = 0;
+      act_fact = act;
+      fact_valid = true;
+      __syncthreads();
       if (sm.flag) {
         if (!cold) { status |= RG_STATUS_NUMERIC; ipm_dead = true; }   // a failed cold start just hands over
         break;
       }
 
-      // gr = P u + q at the particular solution (u0 = 0 in the first cold round)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) up[d] = u0[d];
-      double gr[3];
-      if (cold && round == 0 && RG_COLD_GUESS_LAST == 0) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) gr[d] = q[d];
-      } else {
-        double pu[3];
-        apply_p<H>(sm, ws, blk, up, pu);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) gr[d] = pu[d] + q[d];
-      }
-      // Pass 0 is the solve, passes 1-2 steps of iterative refinement.  The active set is checked after
-      // each: when it moves after pass 0 the refinement would be wasted (the next round starts over),
+      // Pass -1 evaluates gr = P u + q at the particular solution, pass 0 is the solve, passes 1-2 steps of iterative
+      // refinement (one call site of apply_p serves all of them).  The active set is checked after
+      // each solve: when it moves after pass 0 the refinement would be wasted (the next round starts over),
       // and it is skipped as well when pass 0 already left a projected gradient at rounding level.
       // A verdict on the set is only taken from a solve that is accurate enough to give it (projected
       // gradient <= 1e-9 |q|): with many active rows at h = 20 a single refinement step can leave 1e-9,
       // above the multiplier-sign threshold, and one weakly active row then flips in and out for ever.
+#pragma unroll
+      for (int d = 0; d < 3; ++d) up[d] = u0[d];
+      double gr[3] = {0.0, 0.0, 0.0};
+      if constexpr (!C::GRAD_IN_PASS_LOOP) {
+        double pu0[3];
+        apply_p<H>(sm, ws, blk, up, pu0);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) gr[d] = pu0[d] + q[d];
+      }
       unsigned act_new = act;
       double nchg = 0.0, ncone = 0.0, pgm = 0.0;
       bool accept = false;
 #pragma unroll 1
-      for (int pass = 0; pass < 3; ++pass) {
-        double ng[3], bprime[3], dx[3], pu[3];
+      for (int pass = C::GRAD_IN_PASS_LOOP ? -1 : 0; pass < 3; ++pass) {
+        double pu[3];
+        if (pass >= 0) {
+          double ng[3], bprime[3], dx[3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) ng[d] = -gr[d];
-        RG_TOC(21);
-        woodbury_solve<H>(sm, blk, mproj, ng, bprime);
-        RG_TOC(22);
-        sym3_mul(mproj, bprime, dx);
+          for (int d = 0; d < 3; ++d) ng[d] = -gr[d];
+          RG_TOC(21);
+          woodbury_solve<H>(sm, blk, mproj, ng, bprime);
+          RG_TOC(22);
+          sym3_mul(mproj, bprime, dx);
 #pragma unroll
-        for (int d = 0; d < 3; ++d) up[d] += dx[d];
+          for (int d = 0; d < 3; ++d) up[d] += dx[d];
+        }
         apply_p<H>(sm, ws, blk, up, pu);
         RG_TOC(23);
 #pragma unroll
         for (int d = 0; d < 3; ++d) gr[d] = pu[d] + q[d];
+        if (pass < 0) continue;
 
         // --- verify: primal feasibility of the rows left out, multiplier signs of the rows held
         act_new = act;
@@ -1995,6 +2023,12 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
           }
           int rmin = -1;
           if constexpr (C::BASIS_IN_REGS) {
+#if RG_REBUILD_BASIS
+            // the basis is rebuilt from the bit mask (a few dozen instructions) instead of being kept live across the
+            // factorisation and the sweeps: 21 doubles fewer in flight over the heavy calls
+            BlockBasis B;
+            { unsigned act_again = act; build_basis(act_again, active_blk, mu, hv_up, lo_b, B); }
+#endif
             // multipliers: sum_i y_i a_i = -gr on span(e)  ->  back substitution with the upper triangular rr
             const int row0 = B.row0, row1 = B.row1, row2 = B.row2;
             const double g0 = -(gr[0] * B.e0[0] + gr[1] * B.e0[1] + gr[2] * B.e0[2]);
@@ -2053,7 +2087,7 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
         // (bits 0-3 / 5-8; bits 4 / 9 are the fz bounds)
         nchg = (double)(__popc(act_new ^ act) + 4096 * __popc((act_new ^ act) & 0x1EFu));
         double dmn = 0.0;
-        block_reduce<C::NW>(nchg, pgm, dmn, sm.red);
+        block_reduce<C::NW, 3>(nchg, pgm, dmn, sm.red);
         ncone = floor(nchg * (1.0 / 4096.0));
         nchg -= 4096.0 * ncone;
         RG_TOC(24);
@@ -2084,7 +2118,7 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
 #pragma unroll
       for (int d = 0; d < 3; ++d) u_out[d] = up[d];
       double cnt = (double)__popc(act), dmx = 0.0, dmn = 0.0;
-      block_reduce<C::NW>(cnt, dmx, dmn, sm.red);
+      block_reduce<C::NW, 1>(cnt, dmx, dmn, sm.red);
       n_active_out = (int)cnt;
       done = true;
       break;
@@ -2105,7 +2139,7 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
         }
         if (!(thmax == thmax)) thmax = 0.0;
       }
-      block_reduce<C::NW>(dsum, dmx, thmax, sm.red);
+      block_reduce<C::NW, 4>(dsum, dmx, thmax, sm.red);
       const double theta = RG_IPM_WARM * thmax;
       if constexpr (!LEAN) {
         if (active_blk && theta > 0.0) {
