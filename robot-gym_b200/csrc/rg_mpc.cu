@@ -42,6 +42,8 @@ extern "C" int rg_debug_set_trace(double* dev_buf, int env) {
   cudaMemcpyToSymbol(g_trace_env, &env, sizeof(env));
   return 0;
 }
+#endif
+#if defined(RG_DEBUG_TRACE) && !defined(RG_DEBUG_TIMELINE_ONLY)
 #define RG_TRACE(slot, value) do { if (g_trace && env == g_trace_env && threadIdx.x == 0) g_trace[slot] = (value); } while (0)
 // phase timers: cycles accumulated in g_trace[900 + phase] by thread 0 of the traced env
 #define RG_TIC() long long rg_t0_ = clock64()
@@ -2095,7 +2097,7 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
         if (nchg > 0.0) { if (trusted) break; else continue; }
         if (pgm <= (pass == 0 ? RG_SKIP_REFINE_TOL : pass == 1 ? 1e-10 : 1e-7) * qscale) { accept = true; break; }
       }
-#ifdef RG_DEBUG_TRACE
+#if defined(RG_DEBUG_TRACE) && !defined(RG_DEBUG_TIMELINE_ONLY)
       {
         double cnt = (double)__popc(act_new), dmx2 = 0.0, dmn2 = 0.0;
         block_reduce<C::NW>(cnt, dmx2, dmn2, sm.red);

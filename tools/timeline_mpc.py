@@ -1,10 +1,10 @@
-"""Per-CTA timeline of one mpc_solve_kernel launch (development helper, GPU, -DRG_DEBUG_TRACE build in ab/).
+"""Per-CTA timeline of one mpc_solve_kernel launch (development helper, GPU, -DRG_DEBUG_TRACE -DRG_DEBUG_TIMELINE_ONLY build in ab/).
 Prints when the waves start, how long cold-start / interior-point envs take under load and what the tail is."""
 import os, sys, ctypes
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 os.makedirs(os.path.join(REPO, "ab"), exist_ok=True)
-os.environ["RG_CUDA_LIB"] = os.path.join(REPO, "ab", "librg_trace.so")
-os.environ["RG_DEBUG_TRACE"] = "1"
+os.environ["RG_CUDA_LIB"] = os.path.join(REPO, "ab", "librg_timeline.so")
+os.environ["RG_DEBUG_TRACE"] = "2"      # start / end stamps only: the phase timers of mode 1 slow the kernel by a third
 sys.path.insert(0, os.path.join(REPO, "robot-gym_b200")); sys.path.insert(0, REPO)
 import numpy as np, torch
 from robot_gym import cuda as rg
