@@ -114,12 +114,19 @@ struct Cfg {
 #endif
   static constexpr bool RICCATI = H >= RG_RICCATI_MIN_H;
   // active-set basis of a block in named registers (no local-memory frame: DRAM traffic = algorithmic bytes) or in small
-  // local arrays (fewer live registers across the heavy phases).  Registers win at h = 10 (4096 envs +1 %, 65536 envs -3 %,
-  // DRAM traffic 3.2 -> 0.6 MB per 4096-env launch); at h = 5 / 20 the extra spills cost 7-9 % (profiles/r02_basis_storage.md).
+  // local arrays indexed by the run-time row count.  With the basis kept live across the heavy phases the registers won
+  // only at h = 10 (profiles/r02_basis_storage.md); since it is rebuilt for the multiplier test (RG_REBUILD_BASIS) they
+  // win everywhere: h = 5 27.2 -> 28.8 M, h = 20 5.72 -> 5.85 M solves/s at 65536 envs.  The array scheme stays as an A/B option.
 #ifndef RG_BASIS_IN_REGS_H10
 #define RG_BASIS_IN_REGS_H10 1
 #endif
-  static constexpr bool BASIS_IN_REGS = (H == 10) && RG_BASIS_IN_REGS_H10;
+#ifndef RG_BASIS_IN_REGS_H5
+#define RG_BASIS_IN_REGS_H5 1
+#endif
+#ifndef RG_BASIS_IN_REGS_H20
+#define RG_BASIS_IN_REGS_H20 1
+#endif
+  static constexpr bool BASIS_IN_REGS = H == 10 ? RG_BASIS_IN_REGS_H10 : (H < 10 ? RG_BASIS_IN_REGS_H5 : RG_BASIS_IN_REGS_H20);
   // the gradient at the particular solution is evaluated as "pass -1" of the solve / refine loop (one inlined copy of
   // apply_p instead of two: less code on the round's path; +1.5 % at h = 10, -3 % at h = 5 where the kernel spills)
 #ifndef RG_GRAD_IN_PASS_LOOP_H10

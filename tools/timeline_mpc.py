@@ -41,6 +41,8 @@ def main():
     for e in order: print(f"     {e:5d} {start[e]:8.1f} {end[e]:8.1f}  {inf[e,0]:2d} {inf[e,1]:2d} {inf[e,2]:3d}")
     for q in (0.25, 0.5, 0.75, 0.9, 0.99): print(f"   {int(q*100)} % of envs done by {np.quantile(end, q):.1f} us; last start {start.max():.1f} us")
     rounds = inf[:, 1]
+    if os.environ.get("RG_TIMELINE_SAVE"):      # raw per-env stamps for offline scheduling experiments
+        np.savez(os.environ["RG_TIMELINE_SAVE"], start=start, end=end, rounds=rounds, smid=tr[:, 2], n_stance=(st.planned_contacts != 0).sum(axis=1))
     for r in range(1, 16):
         sel = cold & (rounds == r)
         if sel.any(): print(f"   cold, {r} rounds: {sel.sum():5d} envs, mean duration {dur[sel].mean():.1f} us")
