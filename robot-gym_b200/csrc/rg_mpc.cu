@@ -152,9 +152,9 @@ struct Smem {
   __align__(16) double pm2[RIC ? 144 : 2];     // P_{t+1} - PG N PG^T before the time update
   __align__(16) double m6[RIC ? 6 : 1][RIC ? 36 : 2];    // 6 x 6 scratch matrices: D, S, U = D S, Y, Y^-1, G
   __align__(16) double t1[RIC ? 72 : 2];       // PG N
-  double rvec[RIC ? H * 6 : 1];                // r_t of the backward sweep of the current solve
+  __align__(16) double rvec[RIC ? H * 6 : 2];   // r_t of the backward sweep of the current solve
   double gt[H * 6];                // g~ : gradient in acceleration space
-  double avec[H * 6];              // W u, right-hand sides and Woodbury solutions
+  __align__(16) double avec[H * 6];   // W u, right-hand sides and Woodbury solutions
   double kvec[H * 6];              // K (W u)
   __align__(16) double blk44[36];  // updated diagonal block of the current Cholesky panel (4x4 or 6x6)
   double bang[4][9];               // A_leg = I_world^-1 [r_leg]x
@@ -927,62 +927,75 @@ template <int H, class SM>
 __device__ RG_HEAVY_INLINE void riccati_solve(SM& sm) {
   const int lane = threadIdx.x & 31;   // one warp runs this routine (sm.solver_warp)
   const int k12 = lane < 12 ? lane : 0, c6 = lane < 6 ? lane : 0;
+  // The 6- and 12-vectors a stage hands from one product to the next go through shared memory (one predicated store,
+  // __syncwarp, 128-bit broadcast loads) instead of one shuffle pair per element and lane: a single warp issues an
+  // instruction every ~4 cycles, and the shuffle version needed 95 / 192 instructions per backward / forward stage.
+  double* __restrict__ bc6 = sm.t1;          // scratch of the factor sweep, free here: [0..5] w or y, [16..27] Phi x
   double p = 0.0;
 #pragma unroll 1
   for (int t = H - 1; t >= 0; --t) {
     const double* __restrict__ pgk = sm.fac_pg[t] + 6 * k12;
     const double* __restrict__ bt = sm.avec + 6 * t;
     const double2 p01 = ldd2(pgk), p23 = ldd2(pgk + 2), p45 = ldd2(pgk + 4);
-    const double b0 = bt[0], b1 = bt[1], b2 = bt[2], b3 = bt[3], b4 = bt[4], b5 = bt[5];
-    const double bc = bt[c6];
-    const double z = (p01.x * b0 + p01.y * b1 + p23.x * b2) + (p23.y * b3 + p45.x * b4 + p45.y * b5) + p;   // (PG b + p)_k
+    const double2 b01 = ldd2(bt), b23 = ldd2(bt + 2), b45 = ldd2(bt + 4);
+    const double z = (p01.x * b01.x + p01.y * b01.y + p23.x * b23.x) + (p23.y * b23.y + p45.x * b45.x + p45.y * b45.y) + p;   // (PG b + p)_k
     const double zs = __shfl_down_sync(kFull, z, 6);
     const double r = 0.5 * z + zs;                        // lanes 0..5: r_c = (Gam^T .)_c
     if (lane < 6) sm.rvec[6 * t + lane] = r;
-    const double r0 = __shfl_sync(kFull, r, 0), r1 = __shfl_sync(kFull, r, 1), r2 = __shfl_sync(kFull, r, 2);
-    const double r3 = __shfl_sync(kFull, r, 3), r4 = __shfl_sync(kFull, r, 4), r5 = __shfl_sync(kFull, r, 5);
+    __syncwarp();
+    const double* __restrict__ rt = sm.rvec + 6 * t;
+    const double2 r01 = ldd2(rt), r23 = ldd2(rt + 2), r45 = ldd2(rt + 4);
     const double* __restrict__ nr = sm.fac_n[t] + 6 * c6;
     const double2 n01 = ldd2(nr), n23 = ldd2(nr + 2), n45 = ldd2(nr + 4);
-    const double w = bc - ((n01.x * r0 + n01.y * r1 + n23.x * r2) + (n23.y * r3 + n45.x * r4 + n45.y * r5));
-    const double w0 = __shfl_sync(kFull, w, 0), w1 = __shfl_sync(kFull, w, 1), w2 = __shfl_sync(kFull, w, 2);
-    const double w3 = __shfl_sync(kFull, w, 3), w4 = __shfl_sync(kFull, w, 4), w5 = __shfl_sync(kFull, w, 5);
-    const double u = p + ((p01.x * w0 + p01.y * w1 + p23.x * w2) + (p23.y * w3 + p45.x * w4 + p45.y * w5));
+    const double bc = c6 == 0 ? b01.x : (c6 == 1 ? b01.y : (c6 == 2 ? b23.x : (c6 == 3 ? b23.y : (c6 == 4 ? b45.x : b45.y))));
+    const double w = bc - ((n01.x * r01.x + n01.y * r01.y + n23.x * r23.x) + (n23.y * r23.y + n45.x * r45.x + n45.y * r45.y));
+    if (lane < 6) bc6[lane] = w;
+    __syncwarp();
+    const double2 w01 = ldd2(bc6), w23 = ldd2(bc6 + 2), w45 = ldd2(bc6 + 4);
+    const double u = p + ((p01.x * w01.x + p01.y * w01.y + p23.x * w23.x) + (p23.y * w23.y + p45.x * w45.x + p45.y * w45.y));
     const double uu = __shfl_up_sync(kFull, u, 6);
     p = lane < 6 ? u : u + uu;                            // Phi^T: (u_pi; u_pi + u_sigma)
+    __syncwarp();                                         // bc6 is rewritten by the next stage
   }
+  // row c6 of the packed symmetric D_t: element offsets inside nblk[t], the same at every stage
+  int doff[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) doff[j] = c6 >= j ? tri(c6, j) : tri(j, c6);
   double x = 0.0;
 #pragma unroll 1
   for (int t = 0; t < H; ++t) {
     const double* __restrict__ pgt = sm.fac_pg[t];
-    const double bc = lane < 6 ? sm.avec[6 * t + lane] : 0.0;   // every lane touches only the slots it writes itself
     const double xs = __shfl_down_sync(kFull, x, 6);
     const double zx = lane < 6 ? x + xs : x;              // Phi x = (pi + sigma; sigma)
+    if (lane < 12) bc6[16 + lane] = zx;
+    __syncwarp();
     double y0 = lane < 6 ? sm.rvec[6 * t + lane] : 0.0, y1 = 0.0, y2 = 0.0;
 #pragma unroll
-    for (int k = 0; k < 12; k += 3) {
-      y0 = fma(pgt[6 * k + c6], __shfl_sync(kFull, zx, k), y0);
-      y1 = fma(pgt[6 * (k + 1) + c6], __shfl_sync(kFull, zx, k + 1), y1);
-      y2 = fma(pgt[6 * (k + 2) + c6], __shfl_sync(kFull, zx, k + 2), y2);
+    for (int k = 0; k < 12; k += 6) {
+      const double2 z01 = ldd2(bc6 + 16 + k), z23 = ldd2(bc6 + 18 + k), z45 = ldd2(bc6 + 20 + k);
+      y0 = fma(pgt[6 * k + c6], z01.x, y0);       y1 = fma(pgt[6 * (k + 1) + c6], z01.y, y1);
+      y2 = fma(pgt[6 * (k + 2) + c6], z23.x, y2); y0 = fma(pgt[6 * (k + 3) + c6], z23.y, y0);
+      y1 = fma(pgt[6 * (k + 4) + c6], z45.x, y1); y2 = fma(pgt[6 * (k + 5) + c6], z45.y, y2);
     }
     const double y = y0 + (y1 + y2);
-    const double q0 = __shfl_sync(kFull, y, 0), q1 = __shfl_sync(kFull, y, 1), q2 = __shfl_sync(kFull, y, 2);
-    const double q3 = __shfl_sync(kFull, y, 3), q4 = __shfl_sync(kFull, y, 4), q5 = __shfl_sync(kFull, y, 5);
+    if (lane < 6) bc6[lane] = y;
+    __syncwarp();
+    const double2 q01 = ldd2(bc6), q23 = ldd2(bc6 + 2), q45 = ldd2(bc6 + 4);
     const double* __restrict__ jr = sm.fac_j[t] + 6 * c6;
     const double2 j01 = ldd2(jr), j23 = ldd2(jr + 2), j45 = ldd2(jr + 4);
-    const double v = (j01.x * q0 + j01.y * q1 + j23.x * q2) + (j23.y * q3 + j45.x * q4 + j45.y * q5);
-    const double v0 = __shfl_sync(kFull, v, 0), v1 = __shfl_sync(kFull, v, 1), v2 = __shfl_sync(kFull, v, 2);
-    const double v3 = __shfl_sync(kFull, v, 3), v4 = __shfl_sync(kFull, v, 4), v5 = __shfl_sync(kFull, v, 5);
+    const double v = (j01.x * q01.x + j01.y * q01.y + j23.x * q23.x) + (j23.y * q23.y + j45.x * q45.x + j45.y * q45.y);
+    const double bc = lane < 6 ? sm.avec[6 * t + lane] : 0.0;   // every lane touches only the slots it writes itself
+    __syncwarp();                                                // everybody has read y before v overwrites bc6[0..5]
+    if (lane < 6) bc6[lane] = v;
+    __syncwarp();
+    const double2 v01 = ldd2(bc6), v23 = ldd2(bc6 + 2), v45 = ldd2(bc6 + 4);
     const double* __restrict__ nb = sm.nblk[t];
-    const double d0 = nb[tri(c6, 0)];                                              // row c6 of the packed symmetric D_t
-    const double d1 = c6 >= 1 ? nb[tri(c6, 1)] : nb[tri(1, c6)];
-    const double d2 = c6 >= 2 ? nb[tri(c6, 2)] : nb[tri(2, c6)];
-    const double d3 = c6 >= 3 ? nb[tri(c6, 3)] : nb[tri(3, c6)];
-    const double d4 = c6 >= 4 ? nb[tri(c6, 4)] : nb[tri(4, c6)];
-    const double d5 = nb[tri(5, c6)];
-    const double a = bc - ((d0 * v0 + d1 * v1 + d2 * v2) + (d3 * v3 + d4 * v4 + d5 * v5));
+    const double a = bc - ((nb[doff[0]] * v01.x + nb[doff[1]] * v01.y + nb[doff[2]] * v23.x) +
+                           (nb[doff[3]] * v23.y + nb[doff[4]] * v45.x + nb[doff[5]] * v45.y));
     const double as = __shfl_up_sync(kFull, a, 6);
     x = lane < 6 ? zx + 0.5 * a : x + as;                 // Phi x + Gam a
     if (lane < 6) sm.avec[6 * t + lane] = v;
+    __syncwarp();                                         // bc6 is rewritten by the next stage
   }
 }
 
