@@ -242,6 +242,12 @@ __device__ __forceinline__ double c1f(int h, int j, int k) { return (double)(h -
 #ifndef RG_IPM_WARM
 #define RG_IPM_WARM 0.99
 #endif
+// multiplier tolerance (relative to the gradient scale) below which a STICKY row -- one that was dropped and came back --
+// is still held: it stops the in / out cycling of weakly active rows, at the price of a point that may sit up to
+// tol / (2 alpha) away from the optimum along a weakly curved direction
+#ifndef RG_STICKY_TOL
+#define RG_STICKY_TOL 1e-9
+#endif
 #ifndef RG_REBUILD_BASIS
 #define RG_REBUILD_BASIS 1
 #endif
@@ -1664,7 +1670,7 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
   const double cold_max_viol = (double)ws->cold_start_max_violations;
   // Weakly active rows (multiplier ~ 0 at the optimum: strict complementarity fails) flip for ever between "dropped
   // because its multiplier is -1e-10" and "violated by 1e-9 without it".  A row that was dropped and came back is
-  // sticky: it then only leaves for a multiplier that is wrong by more than 1e-7 of the gradient scale.
+  // sticky: it then only leaves for a multiplier that is wrong by more than RG_STICKY_TOL (1e-9) of the gradient scale.
   unsigned dropped_rows = 0u, sticky_rows = 0u;
 #pragma unroll 1
   for (int attempt = (cold_rounds > 0 && !skip_cold) ? -1 : 0; attempt < (LEAN ? 0 : 3) && !done; ++attempt) {
@@ -2067,7 +2073,7 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
               if (i < na) {
                 // upper-bound rows need y >= 0, lower-bound rows y <= 0
                 const double ysgn = row < 5 ? yi : -yi;
-                const double drop_tol = ((sticky_rows >> row) & 1u) ? 1e-7 : 1e-10;
+                const double drop_tol = ((sticky_rows >> row) & 1u) ? RG_STICKY_TOL : 1e-10;
                 if (ysgn < -drop_tol * qscale) { act_new &= ~(1u << row); dropped_rows |= 1u << row; }
                 if (ysgn < ymin) { ymin = ysgn; rmin = row; }
               }
@@ -2088,7 +2094,7 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
             for (int i = 0; i < na; ++i) {
               // upper-bound rows need y >= 0, lower-bound rows y <= 0
               const double ysgn = rows[i] < 5 ? y[i] : -y[i];
-              const double drop_tol = ((sticky_rows >> rows[i]) & 1u) ? 1e-7 : 1e-10;
+              const double drop_tol = ((sticky_rows >> rows[i]) & 1u) ? RG_STICKY_TOL : 1e-10;
               if (ysgn < -drop_tol * qscale) { act_new &= ~(1u << rows[i]); dropped_rows |= 1u << rows[i]; }
               if (ysgn < ymin) { ymin = ysgn; imin = i; }
             }
