@@ -415,3 +415,4 @@ def test_weakly_active_row_does_not_cycle(rg_lib, cuda_device):
         assert np.all(info[:, rg.RG_INFO_STATUS] & rg.RG_STATUS_POLISHED), info
         ref = _numpy_oracle(st, 3, 10)
         assert np.abs(hf[3].reshape(-1) - ref).max() < REL_TOL * max(1.0, np.abs(ref).max())
+
