@@ -1454,7 +1454,12 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
     const int c = tid / 3, d = tid % 3;
     double v = 0.0;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) v += ws->w_rho[r] * tm[3 * r + c] * tm[3 * r + d];
+    for (int r = 0; r < 3; ++r) {
+      // columns c and d of T by selects (a run-time index would put tm[] into local memory)
+      const double tc = c == 0 ? tm[3 * r] : (c == 1 ? tm[3 * r + 1] : tm[3 * r + 2]);
+      const double td = d == 0 ? tm[3 * r] : (d == 1 ? tm[3 * r + 1] : tm[3 * r + 2]);
+      v += ws->w_rho[r] * tc * td;
+    }
     sm.k2ang[tid] = 2.0 * dt4 * v;
   }
   if (tid < 6) sm.k1[tid] = 2.0 * dt2 * ws->w_nu[tid];
@@ -1501,7 +1506,10 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
           for (int c = 0; c < 3; ++c) v += tmp[3 * a + c] * rb[3 * b + c];
           iw[3 * a + b] = v;
         }
-      const double rx = fw[tid][0], ry = fw[tid][1], rz = fw[tid][2];
+      // own leg's lever arm by selects: a run-time index into fw[][] would put it (and in_feet[]) into a local-memory frame
+      const double rx = tid == 0 ? fw[0][0] : (tid == 1 ? fw[1][0] : (tid == 2 ? fw[2][0] : fw[3][0]));
+      const double ry = tid == 0 ? fw[0][1] : (tid == 1 ? fw[1][1] : (tid == 2 ? fw[2][1] : fw[3][1]));
+      const double rz = tid == 0 ? fw[0][2] : (tid == 1 ? fw[1][2] : (tid == 2 ? fw[2][2] : fw[3][2]));
       const double sk[9] = {0.0, -rz, ry, rz, 0.0, -rx, -ry, rx, 0.0};
 #pragma unroll
       for (int a = 0; a < 3; ++a)
