@@ -248,6 +248,10 @@ __device__ __forceinline__ double c1f(int h, int j, int k) { return (double)(h -
 #ifndef RG_STICKY_TOL
 #define RG_STICKY_TOL 1e-9
 #endif
+// programmatic dependent launch of the fallback kernel behind the lean kernel (launch_h)
+#ifndef RG_PDL
+#define RG_PDL 1
+#endif
 #ifndef RG_REBUILD_BASIS
 #define RG_REBUILD_BASIS 1
 #endif
@@ -2250,6 +2254,9 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, RgMpcScratch* __restrict__ scr
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<H>& sm = *reinterpret_cast<Smem<H>*>(smem_raw);
   const int env = blockIdx.x;
+#if RG_PDL
+  if constexpr (LEAN) asm volatile("griddepcontrol.launch_dependents;");   // see launch_h: the fallback grid may be scheduled behind us
+#endif
   if (env >= n_env) return;
   solve_env<H, LEAN>(sm, ws, scratch, env, false, io);
 }
@@ -2263,6 +2270,9 @@ __global__ void __launch_bounds__(Cfg<H>::NT, Cfg<H>::MIN_BLOCKS)
 mpc_fallback_kernel(const RgMpcDev* __restrict__ ws, RgMpcScratch* __restrict__ scratch, int n_env, const rg_mpc_io io) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<H>& sm = *reinterpret_cast<Smem<H>*>(smem_raw);
+#if RG_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched programmatically: the lean grid must have completed
+#endif
   const int count = min(scratch->queue_tail, min(scratch->capacity, n_env));
   for (int q = blockIdx.x; q < count; q += gridDim.x) {
     const int env = scratch->queue[q];
@@ -2341,9 +2351,26 @@ int launch_h(const RgMpcDev* ws, int n_env, const rg_mpc_io& io, int two_kernel,
     rc = rg_check_cuda(cudaGetLastError(), "mpc_solve_kernel (lean) launch");
     if (rc != RG_OK) return rc;
     const int grid = n_env < slots ? n_env : slots;       // as many CTAs as fit at once: an empty queue costs one wave of exits
+#if RG_PDL
+    // Programmatic dependent launch: every lean CTA signals at its start, so once the last one HAS STARTED the fallback
+    // grid may take the slots the draining lean grid leaves free; its CTAs block in griddepcontrol.wait until the lean
+    // grid has completed (queue visible).  The launch latency of the second kernel hides behind the first one's tail.
+    {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)Cfg<H>::NT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      const cudaError_t e = cudaLaunchKernelEx(&cfg, mpc_fallback_kernel<H>, ws, scratch, n_env, io);
+      rg_count_launch();
+      return rg_check_cuda(e != cudaSuccess ? e : cudaGetLastError(), "mpc_fallback_kernel launch");
+    }
+#else
     mpc_fallback_kernel<H><<<grid, Cfg<H>::NT, smem, stream>>>(ws, scratch, n_env, io);
     rg_count_launch();
     return rg_check_cuda(cudaGetLastError(), "mpc_fallback_kernel launch");
+#endif
   }
   rc = configure_kernel((const void*)mpc_solve_kernel<H, false>, smem, Cfg<H>::MIN_BLOCKS, "cudaFuncSetAttribute(mpc_solve_kernel)");
   if (rc != RG_OK) return rc;
