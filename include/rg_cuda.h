@@ -94,8 +94,10 @@ typedef struct rg_mpc_params {
                                   more violated friction-cone rows than this; 0 (default) = no limit */
   int32_t two_kernel_solve;    /* 1 (default): a lean active-set-only kernel solves every env and queues the ones its
                                   rounds cannot verify; the complete solver (interior point, escalation) then runs on
-                                  that list only.  0: one kernel with the complete solver for every env.  Same
-                                  results either way; needs cold_start_rounds > 0 and a workspace sized for n_env. */
+                                  that list only (launched programmatically behind the first kernel, so that its
+                                  launch latency hides behind the first grid's tail).  0: one kernel with the complete
+                                  solver for every env.  Same results either way; needs cold_start_rounds > 0 and a
+                                  workspace sized for n_env. */
   int32_t reserved_;
 } rg_mpc_params;
 
