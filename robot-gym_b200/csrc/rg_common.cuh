@@ -95,7 +95,27 @@ extern "C" uint64_t rg_launch_count(void);
 
 // launchers implemented in the .cu files
 struct rg_controller_state;
-int rg_launch_mpc(const RgMpcDev* ws, int horizon, int n_env, const rg_mpc_io& io, int two_kernel, cudaStream_t stream);
+// chained = 1: the caller launched a kernel that signals griddepcontrol.launch_dependents right before (the step
+// prologue) and launches one with the programmatic attribute right after (the epilogue): the first MPC kernel is then
+// launched programmatically too.  Every MPC kernel starts with griddepcontrol.wait (a no-op after a plain launch).
+int rg_launch_mpc(const RgMpcDev* ws, int horizon, int n_env, const rg_mpc_io& io, int two_kernel, cudaStream_t stream, int chained = 0);
+
+// Kernel launch with or without the programmatic-stream-serialization attribute (programmatic dependent launch: the
+// grid may become resident while its predecessor drains; it must execute griddepcontrol.wait before touching the
+// predecessor's results, and the predecessor signals with griddepcontrol.launch_dependents).
+template <class... KArgs, class... Args>
+inline cudaError_t rg_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool programmatic, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = programmatic ? 1 : 0;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+#define RG_GRID_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define RG_GRID_LAUNCH_DEPENDENTS() asm volatile("griddepcontrol.launch_dependents;")
 // host-side record of a workspace prepared by rg_mpc_setup (no device access on the launch path)
 struct RgMpcHostInfo { int horizon; int queue_capacity; int two_kernel; };
 int rg_mpc_workspace_info(const void* workspace, RgMpcHostInfo* info);

@@ -2255,7 +2255,8 @@ mpc_solve_kernel(const RgMpcDev* __restrict__ ws, RgMpcScratch* __restrict__ scr
   Smem<H>& sm = *reinterpret_cast<Smem<H>*>(smem_raw);
   const int env = blockIdx.x;
 #if RG_PDL
-  if constexpr (LEAN) asm volatile("griddepcontrol.launch_dependents;");   // see launch_h: the fallback grid may be scheduled behind us
+  RG_GRID_LAUNCH_DEPENDENTS();   // see launch_h: the fallback grid (lean) or the step epilogue (complete kernel) may be scheduled behind us
+  RG_GRID_WAIT();                // launched programmatically behind the step prologue in rg_control_step; a no-op otherwise
 #endif
   if (env >= n_env) return;
   solve_env<H, LEAN>(sm, ws, scratch, env, false, io);
@@ -2271,7 +2272,8 @@ mpc_fallback_kernel(const RgMpcDev* __restrict__ ws, RgMpcScratch* __restrict__ 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<H>& sm = *reinterpret_cast<Smem<H>*>(smem_raw);
 #if RG_PDL
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched programmatically: the lean grid must have completed
+  RG_GRID_LAUNCH_DEPENDENTS();   // the step epilogue may be scheduled behind this grid
+  RG_GRID_WAIT();                // launched programmatically: the lean grid must have completed
 #endif
   const int count = min(scratch->queue_tail, min(scratch->capacity, n_env));
   for (int q = blockIdx.x; q < count; q += gridDim.x) {
@@ -2333,7 +2335,7 @@ int sm_count() {
 }
 
 template <int H>
-int launch_h(const RgMpcDev* ws, int n_env, const rg_mpc_io& io, int two_kernel, cudaStream_t stream) {
+int launch_h(const RgMpcDev* ws, int n_env, const rg_mpc_io& io, int two_kernel, cudaStream_t stream, int chained) {
   const size_t smem = sizeof(Smem<H>);
   RgMpcScratch* scratch = (RgMpcScratch*)((char*)ws + RG_MPC_SCRATCH_OFFSET);
   int rc;
@@ -2346,37 +2348,25 @@ int launch_h(const RgMpcDev* ws, int n_env, const rg_mpc_io& io, int two_kernel,
     if (rc != RG_OK) return rc;
     rc = configure_kernel((const void*)mpc_fallback_kernel<H>, smem, Cfg<H>::MIN_BLOCKS, "cudaFuncSetAttribute(mpc_fallback_kernel)");
     if (rc != RG_OK) return rc;
-    mpc_solve_kernel<H, true><<<n_env, Cfg<H>::NT, smem, stream>>>(ws, scratch, n_env, io);
+    rc = rg_check_cuda(rg_launch(mpc_solve_kernel<H, true>, dim3((unsigned)n_env), dim3((unsigned)Cfg<H>::NT), smem, stream,
+                                 RG_PDL && chained, ws, scratch, n_env, io), "mpc_solve_kernel (lean) launch");
     rg_count_launch();
-    rc = rg_check_cuda(cudaGetLastError(), "mpc_solve_kernel (lean) launch");
     if (rc != RG_OK) return rc;
     const int grid = n_env < slots ? n_env : slots;       // as many CTAs as fit at once: an empty queue costs one wave of exits
-#if RG_PDL
     // Programmatic dependent launch: every lean CTA signals at its start, so once the last one HAS STARTED the fallback
     // grid may take the slots the draining lean grid leaves free; its CTAs block in griddepcontrol.wait until the lean
     // grid has completed (queue visible).  The launch latency of the second kernel hides behind the first one's tail.
-    {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)Cfg<H>::NT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = attr; cfg.numAttrs = 1;
-      const cudaError_t e = cudaLaunchKernelEx(&cfg, mpc_fallback_kernel<H>, ws, scratch, n_env, io);
-      rg_count_launch();
-      return rg_check_cuda(e != cudaSuccess ? e : cudaGetLastError(), "mpc_fallback_kernel launch");
-    }
-#else
-    mpc_fallback_kernel<H><<<grid, Cfg<H>::NT, smem, stream>>>(ws, scratch, n_env, io);
+    rc = rg_check_cuda(rg_launch(mpc_fallback_kernel<H>, dim3((unsigned)grid), dim3((unsigned)Cfg<H>::NT), smem, stream, RG_PDL != 0,
+                                 ws, scratch, n_env, io), "mpc_fallback_kernel launch");
     rg_count_launch();
-    return rg_check_cuda(cudaGetLastError(), "mpc_fallback_kernel launch");
-#endif
+    return rc;
   }
   rc = configure_kernel((const void*)mpc_solve_kernel<H, false>, smem, Cfg<H>::MIN_BLOCKS, "cudaFuncSetAttribute(mpc_solve_kernel)");
   if (rc != RG_OK) return rc;
-  mpc_solve_kernel<H, false><<<n_env, Cfg<H>::NT, smem, stream>>>(ws, scratch, n_env, io);
+  rc = rg_check_cuda(rg_launch(mpc_solve_kernel<H, false>, dim3((unsigned)n_env), dim3((unsigned)Cfg<H>::NT), smem, stream,
+                               RG_PDL && chained, ws, scratch, n_env, io), "mpc_solve_kernel launch");
   rg_count_launch();
-  return rg_check_cuda(cudaGetLastError(), "mpc_solve_kernel launch");
+  return rc;
 }
 
 
@@ -2474,11 +2464,11 @@ extern "C" int rg_debug_riccati_solve(int horizon, const double* k1, const doubl
   }
 }
 
-int rg_launch_mpc(const RgMpcDev* ws, int horizon, int n_env, const rg_mpc_io& io, int two_kernel, cudaStream_t stream) {
+int rg_launch_mpc(const RgMpcDev* ws, int horizon, int n_env, const rg_mpc_io& io, int two_kernel, cudaStream_t stream, int chained) {
   switch (horizon) {
-    case 5: return launch_h<5>(ws, n_env, io, two_kernel, stream);
-    case 10: return launch_h<10>(ws, n_env, io, two_kernel, stream);
-    case 20: return launch_h<20>(ws, n_env, io, two_kernel, stream);
+    case 5: return launch_h<5>(ws, n_env, io, two_kernel, stream, chained);
+    case 10: return launch_h<10>(ws, n_env, io, two_kernel, stream, chained);
+    case 20: return launch_h<20>(ws, n_env, io, two_kernel, stream, chained);
     default:
       rg_set_error("unsupported horizon %d (kernels are built for 5, 10, 20)", horizon);
       return RG_ERR_UNSUPPORTED;

@@ -391,6 +391,7 @@ __global__ void pack_kernel(const RgRobotDev* __restrict__ R, int n_env, const i
 // Prologue: gait + estimator + swing latch/target + IK.  One thread per env (the estimator state is
 // per env; the four legs are unrolled).  Epilogue: J^T force -> torque + pack, one thread per leg.
 __global__ void step_prologue_kernel(const RgRobotDev* __restrict__ R, int n_env, rg_controller_state s) {
+  RG_GRID_LAUNCH_DEPENDENTS();   // the solve kernel is launched programmatically behind this grid (rg_control_step)
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= n_env) return;
   double vb[3], vw[3];
@@ -432,6 +433,7 @@ __global__ void step_prologue_kernel(const RgRobotDev* __restrict__ R, int n_env
 }
 
 __global__ void step_epilogue_kernel(const RgRobotDev* __restrict__ R, int n_env, rg_controller_state s) {
+  RG_GRID_WAIT();                // launched programmatically behind the last solve kernel: its forces must be complete
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 4 * n_env) return;
   const int leg = idx & 3;
@@ -755,11 +757,14 @@ extern "C" int rg_control_step(const void* mpc_ws, const void* robot_ws, int n_e
   io.solve_info = s->solve_info;
   io.active_set_io = s->mpc_active_set;
   io.zero_yaw = 1;
-  rc = rg_launch_mpc((const RgMpcDev*)mpc_ws, info.horizon, n_env, io, info.two_kernel && info.queue_capacity >= n_env, st);
+  // prologue -> solve kernel(s) -> epilogue are chained by programmatic dependent launches: each grid becomes resident
+  // while its predecessor drains and waits (griddepcontrol.wait) for it to complete, so the launch latencies overlap
+  rc = rg_launch_mpc((const RgMpcDev*)mpc_ws, info.horizon, n_env, io, info.two_kernel && info.queue_capacity >= n_env, st, 1);
   if (rc != RG_OK) return rc;
-  step_epilogue_kernel<<<grid_for(4 * n_env, 256), 256, 0, st>>>((const RgRobotDev*)robot_ws, n_env, *s);
+  rc = rg_check_cuda(rg_launch(step_epilogue_kernel, dim3((unsigned)grid_for(4 * n_env, 256)), dim3(256), 0, st, true,
+                               (const RgRobotDev*)robot_ws, n_env, *s), "step_epilogue_kernel launch");
   rg_count_launch();
-  return rg_check_cuda(cudaGetLastError(), "step_epilogue_kernel launch");
+  return rc;
 }
 
 // ---- the control step as ONE graph launch ---------------------------------------------------------------------------
