@@ -92,8 +92,11 @@ struct Cfg {
 #ifndef RG_CHOL_W_H10
 #define RG_CHOL_W_H10 4
 #endif
+// resident CTAs per SM at h = 10 (launch bound and shared-memory carveout).  8 until the instruction-count pass of round 2
+// had loaded the shared-memory pipe to 60 % of its wavefront peak; since then 7 is faster (+2.5 % at 65536 envs, +3.5 %
+// at 4096, where 4096 / (148 x 7) is almost a whole number of waves); 6: -6 %, 9: -4 %.
 #ifndef RG_MIN_BLOCKS_H10
-#define RG_MIN_BLOCKS_H10 8
+#define RG_MIN_BLOCKS_H10 7
 #endif
 // the two heavy routines: one out-of-line copy each (default) or inlined at their call sites (A/B)
 #ifndef RG_HEAVY_INLINE
@@ -545,7 +548,7 @@ __device__ RG_HEAVY_INLINE void cholesky_rows_w(SM& sm, int j_begin) {
 // stop changing at its own step: every lane solves its own diagonal block ONCE after the sweep), and the
 // pivot rows of the backward sweep are addressed by additions.  27 / 30 instructions per step instead of
 // 40 / 45 (tools/microbench/chol_bench.cu t5: 6.2k cycles per solve alone on an SM against 9.3k, 11.1k
-// against 14.0k with 8 CTAs per SM; one pivot per step with strided rows: 14.8k).
+// against 14.0k with 8 CTAs resident per SM; one pivot per step with strided rows: 14.8k).
 // T(i) mod 16 is a permutation over the even and over the odd rows of 16 consecutive lanes, so the
 // per-column loads stay bank-conflict free with this ownership too.
 template <int H, class SM>
