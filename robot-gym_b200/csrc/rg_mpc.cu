@@ -21,13 +21,19 @@
 //    time blocks whose rows moved.  Problems on which the rounds cycle fall back to a Mehrotra
 //    predictor-corrector interior point from a strictly feasible start, which hands its active rows
 //    back to the rounds; an escalation ladder drives the interior point deeper when they do not verify.
+//  * Two kernels per solve: mpc_solve_kernel<H, LEAN = true> holds the active-set rounds only and
+//    queues the envs they do not verify; mpc_fallback_kernel<H> (the complete solver) runs on that queue, launched
+//    programmatically behind the first.  Batches that fit one wave of CTAs run mpc_solve_kernel<H, false> alone.
+//  * h = 20 factorises Psi by a Riccati sweep over the horizon instead of the dense Cholesky.
+//  * A warp alone on its scheduler issues one instruction every ~4 cycles: the serial phases (sweeps, late Cholesky
+//    panels) are written for instruction COUNT, not for short dependent chains.
 //
-// Thread roles inside a CTA (NT = 32 * ceil(6h / 32) threads):
-//   "block" threads  tid < 4h : own one (time step, leg) force triple with its 10 slacks and
-//                               multipliers in registers; 4 adjacent lanes = the 4 legs of a step,
+// Thread roles inside a CTA (NT = 32 * ceil(6h / 32) threads on the dense path, 32 * ceil(4h / 32) on the Riccati path):
+//   "block" threads  tid < 4h : own one (time step, leg) force triple (and, in the complete solver only, its 10
+//                               slacks and multipliers) in registers; 4 adjacent lanes = the 4 legs of a step,
 //                               so per-step sums over legs are two __shfl_xor rounds.
 //   "row"   threads  tid < 6h : own one row of Psi during the Cholesky factorisation.
-//   warp 0                    : runs the two triangular sweeps with __shfl broadcasts.
+//   one warp (rotated over the SM sub-partitions, sm.solver_warp) runs the triangular / Riccati sweeps.
 #include "rg_common.cuh"
 #include <math.h>
 #include <map>
