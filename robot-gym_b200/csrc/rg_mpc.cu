@@ -1390,20 +1390,27 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
   // ---------------------------------------------------------------- per-env inputs
   // every load is issued here, before anything depends on one of them: one DRAM latency, not four
   const unsigned contact_word = *reinterpret_cast<const unsigned*>(g_contacts + 4 * (size_t)env);
-  const float in_roll = g_rpy[3 * (size_t)env + 0], in_pitch = g_rpy[3 * (size_t)env + 1], in_yaw = g_rpy[3 * (size_t)env + 2];
-  // the twelve foot coordinates of an env are 48 contiguous, 16-byte aligned bytes: three 128-bit loads
-  float in_feet[12];
-  {
+  // The attitude, the feet, the rates and the command are consumed by threads of warp 0 only (setup_warp below): the
+  // other warps do not load them.  The twelve foot coordinates of an env are 48 contiguous, 16-byte aligned bytes:
+  // three 128-bit loads.
+  float in_roll = 0.f, in_pitch = 0.f, in_yaw = 0.f, in_com_h = 0.f;
+  float in_feet[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float in_w[3] = {0.f, 0.f, 0.f}, in_v[3] = {0.f, 0.f, 0.f}, in_cmd[3] = {0.f, 0.f, 0.f};
+  if (tid < 32) {
+    in_roll = g_rpy[3 * (size_t)env + 0]; in_pitch = g_rpy[3 * (size_t)env + 1]; in_yaw = g_rpy[3 * (size_t)env + 2];
     const float4* __restrict__ f4 = reinterpret_cast<const float4*>(g_feet + 12 * (size_t)env);
     const float4 fa = f4[0], fb = f4[1], fc = f4[2];
     in_feet[0] = fa.x; in_feet[1] = fa.y; in_feet[2] = fa.z; in_feet[3] = fa.w;
     in_feet[4] = fb.x; in_feet[5] = fb.y; in_feet[6] = fb.z; in_feet[7] = fb.w;
     in_feet[8] = fc.x; in_feet[9] = fc.y; in_feet[10] = fc.z; in_feet[11] = fc.w;
+    if (g_com_height) in_com_h = g_com_height[env];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      in_w[a] = g_rpy_rate[3 * (size_t)env + a];
+      in_v[a] = g_com_vel[3 * (size_t)env + a];
+      in_cmd[a] = g_cmd[3 * (size_t)env + a];
+    }
   }
-  const float in_com_h = g_com_height ? g_com_height[env] : 0.f;
-  const float in_w[3] = {g_rpy_rate[3 * (size_t)env + 0], g_rpy_rate[3 * (size_t)env + 1], g_rpy_rate[3 * (size_t)env + 2]};
-  const float in_v[3] = {g_com_vel[3 * (size_t)env + 0], g_com_vel[3 * (size_t)env + 1], g_com_vel[3 * (size_t)env + 2]};
-  const float in_cmd[3] = {g_cmd[3 * (size_t)env + 0], g_cmd[3 * (size_t)env + 1], g_cmd[3 * (size_t)env + 2]};
   const unsigned warm_act = (g_active && is_blk) ? (unsigned)g_active[(size_t)env * C::NB + tid] : (unsigned)RG_ACTIVE_SET_UNKNOWN;
   // stage the rank-h weights of K^-1 (host table) in the Psi buffer, which is free until the first factorisation
   if constexpr (!C::RICCATI) {
