@@ -8,6 +8,8 @@
     solution must satisfy its KKT conditions (stationarity, primal feasibility, multiplier signs) -- no oracle
     solver is involved in that check;
   * the full control step over 256 envs x 10 control steps against the restated LocomotionController;
+  * six random parameter sets (body, weights, regularisation, planning step, friction coefficients, horizon, schedule),
+    384 envs each, every env against the C oracle built from the same parameters;
   * the standalone entry points the fused step does not exercise (rg_swing_targets, rg_com_velocity_update,
     rg_pack_hybrid_action, plain rg_mpc_build_solve), stream re-entrancy, the two-kernel / one-kernel solve.
 
@@ -416,3 +418,43 @@ def test_weakly_active_row_does_not_cycle(rg_lib, cuda_device):
         ref = _numpy_oracle(st, 3, 10)
         assert np.abs(hf[3].reshape(-1) - ref).max() < REL_TOL * max(1.0, np.abs(ref).max())
 
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_random_parameter_sets_every_env_against_the_oracle(rg_lib, cuda_device, seed):
+    """The recalled third-party constants are run-time parameters: random bodies (mass, full inertia
+    tensor), MPC weights, regularisation, planning step, friction coefficients (one per pyramid row), horizon and
+    contact schedule -- 384 envs per set, every env against the C oracle built from the same parameters."""
+    rng = np.random.default_rng(1000 + seed)
+    horizon = int(rng.choice([5, 10, 20]))
+    schedule = str(rng.choice(["trot", "walk", "pace"]))
+    mass = float(rng.uniform(8.0, 40.0))
+    a = rng.normal(size=(3, 3)) * 0.05
+    inertia = (np.diag(rng.uniform(0.05, 0.8, 3)) + a @ a.T)                     # symmetric positive definite
+    base_w = np.array([5, 5, 0.2, 0, 0, 10, 0.5, 0.5, 0.2, 0.2, 0.2, 0.1, 0], dtype=np.float64)
+    weights = tuple(float(x) for x in base_w * rng.uniform(0.3, 3.0, 13))
+    mp = cm.MpcParams(mass=mass, inertia=tuple(float(x) for x in inertia.reshape(-1)), horizon=horizon,
+                      dt=float(rng.uniform(0.02, 0.04)), weights=weights, alpha=float(10 ** rng.uniform(-5.5, -4.5)),
+                      friction_coeffs=tuple(float(x) for x in rng.uniform(0.3, 0.8, 4)))
+    desc = with_gait(GHOST, schedule)
+    st = synthetic.make_states(384, desc, schedule_ctrl=desc.GetCtrlConstants(), seed=2000 + seed)
+    height = GHOST.GetCtrlConstants().MPC_BODY_HEIGHT
+    overrides = dict(mass=mp.mass, inertia=mp.inertia, dt=mp.dt, weights=mp.weights, alpha=mp.alpha,
+                     friction_coeffs=mp.friction_coeffs, fz_max=mp.fz_max, fz_min=mp.fz_min)
+    f, hf, info, _ = _solve(cuda_device, st, horizon=horizon, want_horizon=True, **overrides)
+    assert np.all(info[:, rg.RG_INFO_STATUS] & (rg.RG_STATUS_POLISHED | rg.RG_STATUS_NO_STANCE))
+    _, ref = c_oracle.solve_batch(mp, st, height, n_threads=CORES, want_horizon=True)[:2]
+    n = len(st)
+    gpu, ref = hf.reshape(n, -1), ref.reshape(n, -1)
+    rel = np.abs(gpu - ref).max(axis=1) / np.maximum(1.0, np.abs(ref).max(axis=1))
+    suspects = np.flatnonzero(rel > RECHECK)
+    assert len(suspects) <= 8, (seed, horizon, schedule, len(suspects), float(rel.max()))
+    for i in suspects:                                                           # the numpy oracle arbitrates
+        i = int(i)
+        exact = cm.compute_contact_forces(mp, st.com_velocity_body[i].astype(np.float64), st.base_rpy[i].astype(np.float64),
+                                          st.base_rpy_rate[i].astype(np.float64), st.planned_contacts[i],
+                                          st.foot_positions_base[i].astype(np.float64), [0, 0, height],
+                                          [float(st.command[i, 0]), float(st.command[i, 1]), 0.0], [0, 0, 0],
+                                          [0, 0, float(st.command[i, 2])])
+        rel[i] = np.abs(gpu[i] - exact).max() / max(1.0, np.abs(exact).max())
+    assert rel.max() < REL_TOL, (seed, horizon, schedule, int(rel.argmax()), float(rel.max()))
