@@ -25,7 +25,7 @@ from oracle import c_oracle, convex_mpc as cm, kinematics, locomotion
 from robot_gym import cuda as rg
 from robot_gym.controllers.mpc.batched_kinematics import robot_params_from_description
 from robot_gym.controllers.mpc.batched_mpc_controller import BatchedMPCController
-from robot_gym.model.robots.descriptions import GHOST, with_gait
+from robot_gym.model.robots.descriptions import GHOST, K3LSO, with_gait
 from robot_gym.model.robots.synthetic_robot import SyntheticRobotBatch
 from robot_gym.util import synthetic
 
@@ -257,14 +257,16 @@ def test_wrapper_rejects_short_misplaced_and_misaligned_tensors(rg_lib, cuda_dev
 
 
 # ------------------------------------------------------------------------------------------------ config 3 at scale
-def test_control_step_256_envs_10_steps_against_the_restated_controller(rg_lib, cuda_device):
-    """BASELINE config[2] in parity form: BatchedMPCController over 256 envs x 10 control steps against one
-    restated LocomotionController per env (oracle/locomotion.py with the C port as its QP solver): gait states and
-    phases bit-exact, estimator, forces, swing targets and the 60-float hybrid actions within tolerance."""
-    n_env, n_steps = 256, 10
-    ctrl = GHOST.GetCtrlConstants()
-    seq = synthetic.make_state_sequence(n_env, n_steps, GHOST, seed=synthetic.SEED + 5)
-    robot = SyntheticRobotBatch(GHOST, seq[0], device=cuda_device)
+@pytest.mark.parametrize("robot_name,n_env,n_steps", [("ghost", 256, 10), ("k3lso", 96, 8)])
+def test_control_step_256_envs_10_steps_against_the_restated_controller(rg_lib, cuda_device, robot_name, n_env, n_steps):
+    """BASELINE config[2] in parity form: BatchedMPCController over 256 envs x 10 control steps (ghost; 96 x 8 with the
+    k3lso constants) against one restated LocomotionController per env (oracle/locomotion.py with the C port as its QP
+    solver): gait states and phases bit-exact, estimator, forces, swing targets and the 60-float hybrid actions within
+    tolerance."""
+    desc = {"ghost": GHOST, "k3lso": K3LSO}[robot_name]
+    ctrl = desc.GetCtrlConstants()
+    seq = synthetic.make_state_sequence(n_env, n_steps, desc, seed=synthetic.SEED + 5)
+    robot = SyntheticRobotBatch(desc, seq[0], device=cuda_device)
     ctl = BatchedMPCController(robot, robot.GetTimeSinceReset)
     acts, des, sta, pha, frc = [], [], [], [], []
     for k in range(n_steps):
@@ -278,7 +280,7 @@ def test_control_step_256_envs_10_steps_against_the_restated_controller(rg_lib, 
         assert int(ctl.unverified_count()) == 0
     worst_f = worst_q = worst_tau = 0.0
     for e in range(n_env):
-        orobot = kinematics.OracleRobot(GHOST)
+        orobot = kinematics.OracleRobot(desc)
         clock = {"t": 0.0}
 
         def load(k):
@@ -310,7 +312,7 @@ def test_control_step_256_envs_10_steps_against_the_restated_controller(rg_lib, 
             worst_q = max(worst_q, np.abs(a[:, 0] - ref[:, 0]).max())
             worst_tau = max(worst_tau, np.abs(a[:, 4] - ref[:, 4]).max() / max(1.0, np.abs(ref[:, 4]).max()))
     assert worst_f < REL_TOL and worst_q < 5e-5 and worst_tau < REL_TOL, (worst_f, worst_q, worst_tau)
-    print(f"[control step 256 x 10] worst force {worst_f:.1e} rel, swing joint target {worst_q:.1e} rad, torque {worst_tau:.1e} rel")
+    print(f"[control step {robot_name} {n_env} x {n_steps}] worst force {worst_f:.1e} rel, swing joint target {worst_q:.1e} rad, torque {worst_tau:.1e} rel")
 
 
 # ------------------------------------------------------------------------------------------------ standalone parts
