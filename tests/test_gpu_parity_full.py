@@ -7,7 +7,9 @@
   * a SOLVER-INDEPENDENT pin: the dense QP is built by oracle.convex_mpc.build_qp and the kernel's float64
     solution must satisfy its KKT conditions (stationarity, primal feasibility, multiplier signs) -- no oracle
     solver is involved in that check;
-  * the full control step over 256 envs x 10 control steps against the restated LocomotionController;
+  * the full control step over 256 envs x 10 control steps (ghost) and 96 x 8 (k3lso) against the restated
+    LocomotionController, and at 65536 envs against a 700-env controller over a subset of the same envs (every env is
+    independent of its batch: gait bit-identical, forces and actions equal to rounding);
   * six random parameter sets (body, weights, regularisation, planning step, friction coefficients, horizon, schedule),
     384 envs each, every env against the C oracle built from the same parameters;
   * the standalone entry points the fused step does not exercise (rg_swing_targets, rg_com_velocity_update,
@@ -460,3 +462,38 @@ def test_random_parameter_sets_every_env_against_the_oracle(rg_lib, cuda_device,
                                           [0, 0, float(st.command[i, 2])])
         rel[i] = np.abs(gpu[i] - exact).max() / max(1.0, np.abs(exact).max())
     assert rel.max() < REL_TOL, (seed, horizon, schedule, int(rel.argmax()), float(rel.max()))
+
+
+def test_control_step_at_65536_envs_is_batch_size_independent(rg_lib, cuda_device):
+    """BASELINE config[2] at its full size: three control steps of one BatchedMPCController over 65536 envs (lean
+    kernel + fallback queue, four launches per step) against a second controller that only sees 700 of those envs
+    (one wave: the single complete kernel, one graph launch).  Every env is independent of its batch: gait states and
+    phases must be bit-identical, forces and actions equal to rounding, and nothing may be left unverified.  The
+    small controller's envs are the ones the 256-env test pins to the restated oracle controller."""
+    import dataclasses
+    n_env, n_steps, n_sub = 65536, 3, 700
+    seq = synthetic.make_state_sequence(n_env, n_steps, GHOST, seed=synthetic.SEED + 9)
+    idx = np.sort(np.random.default_rng(7).choice(n_env, n_sub, replace=False))
+    sub = [type(s)(**{f.name: getattr(s, f.name)[idx] for f in dataclasses.fields(s)}) for s in seq]
+    out = []
+    for states in (seq, sub):
+        robot = SyntheticRobotBatch(GHOST, states[0], device=cuda_device)
+        ctl = BatchedMPCController(robot, robot.GetTimeSinceReset)
+        rec = []
+        for k in range(n_steps):
+            robot.load(states[k])
+            ctl.command.copy_(torch.from_numpy(states[k].command).to(cuda_device))
+            a = ctl.get_action()
+            torch.cuda.synchronize()
+            assert int(ctl.unverified_count()) == 0
+            rec.append((a.cpu().numpy().copy(), ctl.leg_state.cpu().numpy().copy(), ctl.normalized_phase.cpu().numpy().copy(),
+                        ctl.contact_forces.cpu().numpy().copy()))
+        out.append(rec)
+    for k in range(n_steps):
+        a_big, s_big, p_big, f_big = out[0][k]
+        a_sub, s_sub, p_sub, f_sub = out[1][k]
+        assert np.array_equal(s_big[idx], s_sub) and p_big[idx].tobytes() == p_sub.tobytes(), k
+        assert np.all(np.isfinite(a_big))
+        scale = np.maximum(1.0, np.abs(f_sub).max(axis=1, keepdims=True))
+        assert (np.abs(f_big[idx] - f_sub) / scale).max() < 1e-6, k
+        assert np.abs(a_big[idx] - a_sub).max() <= 1e-5 * max(1.0, np.abs(a_sub).max()), k
