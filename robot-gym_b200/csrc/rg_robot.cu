@@ -161,26 +161,22 @@ __device__ __forceinline__ void neumaier(double& sum, double& corr, double value
   sum = new_sum;
 }
 
-__device__ __forceinline__ void com_velocity_env(const RgRobotDev& R, int env, const float* __restrict__ vel_world,
-                                                 const float* __restrict__ quat, double* window, double* wsum,
-                                                 double* wcorr, int32_t* wcount, int32_t* whead,
-                                                 double* v_body, double* v_world) {
-  const int W = R.velocity_window;
-  int count = wcount[env], head = whead[env];
-  for (int a = 0; a < 3; ++a) {
-    double* win = window + ((size_t)env * 3 + a) * W;
-    double sum = wsum[3 * (size_t)env + a], corr = wcorr[3 * (size_t)env + a];
-    const double nv = (double)vel_world[3 * (size_t)env + a];
-    if (count >= W) neumaier(sum, corr, -win[head]);   // deque is full: drop the oldest sample
-    neumaier(sum, corr, nv);
-    win[head] = nv;
-    wsum[3 * (size_t)env + a] = sum;
-    wcorr[3 * (size_t)env + a] = corr;
-    v_world[a] = __ddiv_rn(__dadd_rn(sum, corr), (double)W);
-  }
-  whead[env] = (head + 1) % W;
-  if (count < W) wcount[env] = count + 1;
-  // body frame: R(q)^T v  (pybullet invertTransform + multiplyTransforms)
+// One axis of the moving-window average: ring-buffer update + Neumaier sums; returns the world-frame average.
+__device__ __forceinline__ double com_velocity_axis(int W, int env, int a, int count, int head, const float* __restrict__ vel_world,
+                                                    double* window, double* wsum, double* wcorr) {
+  double* win = window + ((size_t)env * 3 + a) * W;
+  double sum = wsum[3 * (size_t)env + a], corr = wcorr[3 * (size_t)env + a];
+  const double nv = (double)vel_world[3 * (size_t)env + a];
+  if (count >= W) neumaier(sum, corr, -win[head]);   // deque is full: drop the oldest sample
+  neumaier(sum, corr, nv);
+  win[head] = nv;
+  wsum[3 * (size_t)env + a] = sum;
+  wcorr[3 * (size_t)env + a] = corr;
+  return __ddiv_rn(__dadd_rn(sum, corr), (double)W);
+}
+
+// body frame: R(q)^T v  (pybullet invertTransform + multiplyTransforms)
+__device__ __forceinline__ void world_to_body(const float* __restrict__ quat, int env, const double* v_world, double* v_body) {
   const double qx = quat[4 * (size_t)env + 0], qy = quat[4 * (size_t)env + 1], qz = quat[4 * (size_t)env + 2], qw = quat[4 * (size_t)env + 3];
   const double d = qx * qx + qy * qy + qz * qz + qw * qw;
   const double s = 2.0 / d;
@@ -189,6 +185,18 @@ __device__ __forceinline__ void com_velocity_env(const RgRobotDev& R, int env, c
   const double m[9] = {1.0 - (yy + zz), xy - wz, xz + wy, xy + wz, 1.0 - (xx + zz), yz - wx, xz - wy, yz + wx, 1.0 - (xx + yy)};
   const V3 vb = mat_tmul(m, v3(v_world[0], v_world[1], v_world[2]));
   v_body[0] = vb.x; v_body[1] = vb.y; v_body[2] = vb.z;
+}
+
+__device__ __forceinline__ void com_velocity_env(const RgRobotDev& R, int env, const float* __restrict__ vel_world,
+                                                 const float* __restrict__ quat, double* window, double* wsum,
+                                                 double* wcorr, int32_t* wcount, int32_t* whead,
+                                                 double* v_body, double* v_world) {
+  const int W = R.velocity_window;
+  const int count = wcount[env], head = whead[env];
+  for (int a = 0; a < 3; ++a) v_world[a] = com_velocity_axis(W, env, a, count, head, vel_world, window, wsum, wcorr);
+  whead[env] = (head + 1) % W;
+  if (count < W) wcount[env] = count + 1;
+  world_to_body(quat, env, v_world, v_body);
 }
 
 __global__ void com_velocity_kernel(const RgRobotDev* __restrict__ R, int n_env, const float* __restrict__ vel_world,
@@ -388,9 +396,68 @@ __global__ void pack_kernel(const RgRobotDev* __restrict__ R, int n_env, const i
 }
 
 // ------------------------------------------------------------------------------------ fused step
-// Prologue: gait + estimator + swing latch/target + IK.  One thread per env (the estimator state is
-// per env; the four legs are unrolled).  Epilogue: J^T force -> torque + pack, one thread per leg.
+// Prologue: gait + estimator + swing latch/target + IK, one thread per (env, leg): the four legs of an env are four
+// adjacent lanes; the estimator's three axes are updated by the lanes of legs 0-2 and handed round with shuffles (a
+// single thread per env did the four legs and three axes one after the other: 4x the dependent chain at N = 1 and a
+// quarter of the threads at large N).  Epilogue: J^T force -> torque + pack, one thread per leg.
 __global__ void step_prologue_kernel(const RgRobotDev* __restrict__ R, int n_env, rg_controller_state s) {
+  RG_GRID_LAUNCH_DEPENDENTS();   // the solve kernel is launched programmatically behind this grid (rg_control_step)
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int env = (int)(idx >> 2), leg = (int)(idx & 3);
+  const bool ok = env < n_env;
+  // estimator: every lane reads the ring-buffer cursor before the lane of leg 3 advances it
+  const int W = R->velocity_window;
+  int count = 0, head = 0;
+  if (ok) { count = s.vel_window_count[env]; head = s.vel_window_head[env]; }
+  __syncwarp();
+  double vw_axis = 0.0;
+  if (ok && leg < 3) vw_axis = com_velocity_axis(W, env, leg, count, head, s.base_velocity_world, s.vel_window, s.vel_window_sum, s.vel_window_corr);
+  if (ok && leg == 3) {
+    s.vel_window_head[env] = (head + 1) % W;
+    if (count < W) s.vel_window_count[env] = count + 1;
+  }
+  const int lane0 = (int)(threadIdx.x & 31u) & ~3;
+  double vw[3];
+  for (int a = 0; a < 3; ++a) vw[a] = __shfl_sync(0xffffffffu, vw_axis, lane0 + a);
+  if (!ok) return;
+  double vb[3];
+  world_to_body(s.base_orientation_xyzw, env, vw, vb);
+  const float vbf[3] = {(float)vb[0], (float)vb[1], (float)vb[2]};
+  if (leg < 3) s.com_velocity_body[3 * (size_t)env + leg] = leg == 0 ? vbf[0] : (leg == 1 ? vbf[1] : vbf[2]);
+  // the swing controller and the MPC read the estimator output as the reference does: float64 in the
+  // reference, float32 state arrays here -> use the float32-rounded value everywhere for consistency
+  const double vbr[3] = {(double)vbf[0], (double)vbf[1], (double)vbf[2]};
+  const double t = s.time_since_reset[env];
+  const double yaw_dot = (double)s.base_rpy_rate[3 * (size_t)env + 2];
+  int d, st;
+  double np;
+  gait_leg(*R, leg, t, s.foot_contacts[idx] != 0, d, st, np);
+  s.desired_leg_state[idx] = d;
+  s.leg_state[idx] = st;
+  s.normalized_phase[idx] = np;
+  s.mpc_contact_state[idx] = (d == RG_LEG_STANCE || d == RG_LEG_EARLY_CONTACT) ? 1 : 0;
+  int32_t ls = s.last_leg_state[idx];
+  double tg[3];
+  const bool has = swing_leg(*R, leg, d, st, np, s.foot_positions_base + 3 * idx, vbr, yaw_dot,
+                             s.command + 3 * (size_t)env, ls, s.phase_switch_foot_local_position + 3 * idx, tg);
+  s.last_leg_state[idx] = ls;
+  if (has) {
+    const float tf[3] = {(float)tg[0], (float)tg[1], (float)tg[2]};
+    double q[3];
+    leg_ik(R->legs[leg], v3(tf[0], tf[1], tf[2]), q);
+    for (int j = 0; j < 3; ++j) {
+      const int m = 3 * leg + j;
+      s.swing_foot_target[3 * idx + j] = tf[j];
+      s.swing_joint_angles[3 * idx + j] = (float)((q[j] - R->motor_offset[m]) * R->motor_direction[m]);
+    }
+    s.swing_joint_valid[idx] = 1;
+  }
+}
+
+// The same prologue with one thread per env (the four legs unrolled): fewer, fatter threads -- the faster mapping for
+// large batches, where the kernel is bound by its FP64 instruction count and per-leg lanes diverge (swing legs run the IK,
+// stance legs idle).  Bit-identical results: both call the same per-leg / per-axis routines.
+__global__ void step_prologue_env_kernel(const RgRobotDev* __restrict__ R, int n_env, rg_controller_state s) {
   RG_GRID_LAUNCH_DEPENDENTS();   // the solve kernel is launched programmatically behind this grid (rg_control_step)
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= n_env) return;
@@ -724,6 +791,13 @@ extern "C" int rg_hybrid_motor_torque_ex(const void* ws, int n_env, const float*
   return rg_check_cuda(cudaGetLastError(), "hybrid_motor_ex_kernel launch");
 }
 
+// Batches up to this many envs run the per-(env, leg) prologue (a quarter of the dependent chain per thread), larger ones
+// the per-env one.  Measured on the B200 (tools/gpu/lat_step.py, warm-started control step): per leg -8 us at 1 ... 1024
+// envs (88 -> 80 us with the Python call), -9 us at 4096, -6 us at 16384, +13 us at 65536.
+#ifndef RG_PROLOGUE_LEG_MAX_ENVS
+#define RG_PROLOGUE_LEG_MAX_ENVS 32768
+#endif
+
 extern "C" int rg_control_step(const void* mpc_ws, const void* robot_ws, int n_env, const rg_controller_state* s, void* stream) {
   if (n_env == 0) return RG_OK;   // empty batch: nothing to validate, nothing to launch
   RG_REQUIRE(mpc_ws && robot_ws && s && n_env >= 0, "rg_control_step");
@@ -737,7 +811,8 @@ extern "C" int rg_control_step(const void* mpc_ws, const void* robot_ws, int n_e
   RG_REQUIRE(!s->applied_motor_torques || s->motor_velocities, "rg_control_step torque consumer (motor_velocities)");
   RG_REQUIRE(((uintptr_t)s->foot_positions_base & 15u) == 0, "rg_control_step foot_positions_base (16-byte alignment)");
   cudaStream_t st = (cudaStream_t)stream;
-  step_prologue_kernel<<<grid_for(n_env, 128), 128, 0, st>>>((const RgRobotDev*)robot_ws, n_env, *s);
+  if (n_env <= RG_PROLOGUE_LEG_MAX_ENVS) step_prologue_kernel<<<grid_for(4 * n_env, 128), 128, 0, st>>>((const RgRobotDev*)robot_ws, n_env, *s);
+  else step_prologue_env_kernel<<<grid_for(n_env, 128), 128, 0, st>>>((const RgRobotDev*)robot_ws, n_env, *s);
   rg_count_launch();
   int rc = rg_check_cuda(cudaGetLastError(), "step_prologue_kernel launch");
   if (rc != RG_OK) return rc;
