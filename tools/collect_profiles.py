@@ -50,4 +50,7 @@ for name in ("bench_n1.json", "bench_reference_n1.json", "configs.json", "timeli
         shutil.copy(os.path.join(src, f"{tag}_{name}"), os.path.join(dst, f"{tag}_{name}"))
 shutil.copy(os.path.join(src, f"{tag}_racecheck.log"), os.path.join(dst, f"{tag}_compute_sanitizer_racecheck.log"))
 shutil.copy(os.path.join(src, f"{tag}_memcheck.log"), os.path.join(dst, f"{tag}_compute_sanitizer_memcheck.log"))
+for tool in ("synccheck", "initcheck"):
+    if os.path.exists(os.path.join(src, f"{tag}_{tool}.log")):
+        shutil.copy(os.path.join(src, f"{tag}_{tool}.log"), os.path.join(dst, f"{tag}_compute_sanitizer_{tool}.log"))
 print("profiles/ updated:", sorted(f for f in os.listdir(dst) if f.startswith(tag + "_")))

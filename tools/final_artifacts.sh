@@ -21,4 +21,5 @@ tools/microbench/chol_bench > $OUT/${TAG}_chol_bench.log 2>&1
 python tools/config1_substitute.py --steps 1000 --numpy-steps 60 --out $OUT/${TAG}_config1_substitute.json > $OUT/${TAG}_config1.log 2>&1
 compute-sanitizer --tool racecheck python tools/sanitize_run.py > $OUT/${TAG}_racecheck.log 2>&1; tail -1 $OUT/${TAG}_racecheck.log
 compute-sanitizer --tool memcheck python tools/sanitize_run.py > $OUT/${TAG}_memcheck.log 2>&1; tail -1 $OUT/${TAG}_memcheck.log
+for tool in synccheck initcheck; do compute-sanitizer --tool $tool python tools/sanitize_run.py > $OUT/${TAG}_$tool.log 2>&1; tail -1 $OUT/${TAG}_$tool.log; done
 ls -la $OUT | grep ${TAG}_
