@@ -464,6 +464,10 @@ def test_random_parameter_sets_every_env_against_the_oracle(rg_lib, cuda_device,
     assert rel.max() < REL_TOL, (seed, horizon, schedule, int(rel.argmax()), float(rel.max()))
 
 
+PROLOGUE_OUTPUTS = ("com_velocity_body", "desired_leg_state", "leg_state", "normalized_phase", "mpc_contact_state", "swing_foot_target",
+                    "swing_joint_angles", "swing_joint_valid", "last_leg_state", "phase_switch_foot_local_position")
+
+
 def test_control_step_at_65536_envs_is_batch_size_independent(rg_lib, cuda_device):
     """BASELINE config[2] at its full size: three control steps of one BatchedMPCController over 65536 envs (lean
     kernel + fallback queue, four launches per step) against a second controller that only sees 700 of those envs
@@ -486,13 +490,18 @@ def test_control_step_at_65536_envs_is_batch_size_independent(rg_lib, cuda_devic
             a = ctl.get_action()
             torch.cuda.synchronize()
             assert int(ctl.unverified_count()) == 0
+            pro = [getattr(ctl, name).cpu().numpy().copy() for name in PROLOGUE_OUTPUTS]
             rec.append((a.cpu().numpy().copy(), ctl.leg_state.cpu().numpy().copy(), ctl.normalized_phase.cpu().numpy().copy(),
-                        ctl.contact_forces.cpu().numpy().copy()))
+                        ctl.contact_forces.cpu().numpy().copy(), pro))
         out.append(rec)
     for k in range(n_steps):
-        a_big, s_big, p_big, f_big = out[0][k]
-        a_sub, s_sub, p_sub, f_sub = out[1][k]
+        a_big, s_big, p_big, f_big, pro_big = out[0][k]
+        a_sub, s_sub, p_sub, f_sub, pro_sub = out[1][k]
         assert np.array_equal(s_big[idx], s_sub) and p_big[idx].tobytes() == p_sub.tobytes(), k
+        # the big batch runs the per-env prologue (step_prologue_env_kernel), the small one the per-(env, leg) mapping:
+        # same routines per leg and per estimator axis, so every prologue output is bit-identical
+        for name, big, small in zip(PROLOGUE_OUTPUTS, pro_big, pro_sub):
+            assert big[idx].tobytes() == small.tobytes(), (k, name)
         assert np.all(np.isfinite(a_big))
         scale = np.maximum(1.0, np.abs(f_sub).max(axis=1, keepdims=True))
         assert (np.abs(f_big[idx] - f_sub) / scale).max() < 1e-6, k
