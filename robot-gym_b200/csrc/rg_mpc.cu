@@ -151,7 +151,7 @@ struct Smem {
   // dense path: Psi and its Cholesky factor
   __align__(16) double psi[RIC ? 2 : Cfg<H>::NPSI];   // lower triangle, row-major, rows padded to even length (prow)
   double kinv_ang[RIC ? 1 : Cfg<H>::NKA];    // K^-1 angular block, packed, index a = 3 j + c
-  double rdiag[RIC ? 1 : Cfg<H>::N6];
+  __align__(16) double rdiag[RIC ? 1 : Cfg<H>::N6];
   // Riccati path (see riccati_factor): per stage P_{t+1} Gam (12 x 6), J_t, N_t (6 x 6), and the sweep's scratch
   // (the dense path declares them with one or two elements: they must not cost it shared memory)
   __align__(16) double fac_pg[RIC ? H : 1][RIC ? 72 : 2];
@@ -348,7 +348,7 @@ __device__ RG_HEAVY_INLINE void cholesky_rows(SM& sm, int j_begin) {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     const bool in_play = row_ok && i >= j0;
     if (in_play) {
-      const double* r2 = row_i;
+      const double* r2 = sm.psi + prow(i);
       const double* p0 = sm.psi + prow(j0);
       const double* p1 = sm.psi + prow(j0 + (w > 1 ? 1 : 0));
       const double* p2 = sm.psi + prow(j0 + (w > 2 ? 2 : 0));
@@ -451,10 +451,17 @@ __device__ RG_HEAVY_INLINE void cholesky_rows(SM& sm, int j_begin) {
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c) if (c < w && j0 + c < i) row_i[j0 + c] = x[c];
-      if (i < j0 + w) {
-        const int r = i - j0;
-        sm.rdiag[i] = r == 0 ? rd[0] : (r == 1 ? rd[1] : (r == 2 ? rd[2] : rd[3]));
-        if (r == 0 && !((rd[0] * rd[1]) * (rd[2] * rd[3]) < 1e300)) sm.flag = 1;
+      if (i == j0) {
+        // every in-play thread holds the block's four inverse pivots: the first panel row publishes all of them (one
+        // thread, two 16-byte stores) instead of every panel row selecting its own
+        if constexpr (N6 % 4 == 0) {
+          *reinterpret_cast<double2*>(sm.rdiag + j0) = make_double2(rd[0], rd[1]);
+          *reinterpret_cast<double2*>(sm.rdiag + j0 + 2) = make_double2(rd[2], rd[3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) if (c < w) sm.rdiag[j0 + c] = rd[c];
+        }
+        if (!((rd[0] * rd[1]) * (rd[2] * rd[3]) < 1e300)) sm.flag = 1;
       }
     }
     RG_TOCL(31, N6 - 1);
