@@ -461,12 +461,15 @@ __device__ RG_HEAVY_INLINE void cholesky_rows(SM& sm, int j_begin) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) if (c < w) sm.rdiag[j0 + c] = rd[c];
         }
-        if (!((rd[0] * rd[1]) * (rd[2] * rd[3]) < 1e300)) sm.flag = 1;
       }
     }
     RG_TOCL(31, N6 - 1);
     __syncthreads();
   }
+  // A non-positive pivot turns its column into NaN / inf and, the matrix being dense, every later pivot with it: one
+  // test of the last two inverse pivots after the loop sees a failure anywhere in the factorisation (it used to cost
+  // ten instructions in every panel).  The caller's barrier publishes the flag.
+  if (i == 0 && !(sm.rdiag[N6 - 2] * sm.rdiag[N6 - 1] < 1e300)) sm.flag = 1;
 }
 
 // Generic W-wide panel variant of cholesky_rows (compiler-scheduled update loop, right-looking factorisation of the
