@@ -1293,7 +1293,7 @@ __device__ __forceinline__ void chol5_block_solve(const Chol5& c, const double* 
 // verification (multipliers) -- instead of being kept live across the heavy phases: 21 doubles fewer in flight.
 struct BlockBasis {
   double e0[3], e1[3], e2[3];
-  double r00, r01, r02, r11, r12, r22;
+  double ir00, r01, r02, ir11, r12, ir22;   // the triangular factor's diagonal is kept as its reciprocals (only ever divided by)
   double bt0, bt1, bt2;
   int row0, row1, row2, na;
 };
@@ -1302,7 +1302,7 @@ __device__ __forceinline__ void build_basis(unsigned& act, bool active_blk, cons
                                             BlockBasis& B) {
 #pragma unroll
   for (int d = 0; d < 3; ++d) { B.e0[d] = 0.0; B.e1[d] = 0.0; B.e2[d] = 0.0; }
-  B.r00 = 1.0; B.r01 = 0.0; B.r02 = 0.0; B.r11 = 1.0; B.r12 = 0.0; B.r22 = 1.0;
+  B.ir00 = 1.0; B.r01 = 0.0; B.r02 = 0.0; B.ir11 = 1.0; B.r12 = 0.0; B.ir22 = 1.0;
   B.bt0 = B.bt1 = B.bt2 = 0.0;
   B.row0 = B.row1 = B.row2 = -1;
   B.na = 0;
@@ -1325,10 +1325,10 @@ __device__ __forceinline__ void build_basis(unsigned& act, bool active_blk, cons
     if (n2 < 1e-18) {
       act &= ~(1u << r);                                               // dependent normal: drop
     } else {
-      const double inrm = rsqrt_pivot(n2), nrm = n2 * inrm;
-      if (B.na == 0) { B.e0[0] = a0 * inrm; B.e0[1] = a1 * inrm; B.e0[2] = a2 * inrm; B.r00 = nrm; B.bt0 = target; B.row0 = r; }
-      else if (B.na == 1) { B.e1[0] = a0 * inrm; B.e1[1] = a1 * inrm; B.e1[2] = a2 * inrm; B.r01 = c0; B.r11 = nrm; B.bt1 = target; B.row1 = r; }
-      else { B.e2[0] = a0 * inrm; B.e2[1] = a1 * inrm; B.e2[2] = a2 * inrm; B.r02 = c0; B.r12 = c1; B.r22 = nrm; B.bt2 = target; B.row2 = r; }
+      const double inrm = rsqrt_pivot(n2);   // 1 / |a|: scales the basis vector and IS the reciprocal diagonal entry
+      if (B.na == 0) { B.e0[0] = a0 * inrm; B.e0[1] = a1 * inrm; B.e0[2] = a2 * inrm; B.ir00 = inrm; B.bt0 = target; B.row0 = r; }
+      else if (B.na == 1) { B.e1[0] = a0 * inrm; B.e1[1] = a1 * inrm; B.e1[2] = a2 * inrm; B.r01 = c0; B.ir11 = inrm; B.bt1 = target; B.row1 = r; }
+      else { B.e2[0] = a0 * inrm; B.e2[1] = a1 * inrm; B.e2[2] = a2 * inrm; B.r02 = c0; B.r12 = c1; B.ir22 = inrm; B.bt2 = target; B.row2 = r; }
       ++B.na;
     }
   }
@@ -1924,9 +1924,9 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
           na = B.na;
           // particular solution u0 = sum_k c_k e_k with a_i . u0 = b_i  (forward substitution with rr^T; unused slots have
           // zero basis vectors and unit diagonal, so they contribute nothing)
-          const double cp0 = na > 0 ? B.bt0 / B.r00 : 0.0;
-          const double cp1 = na > 1 ? (B.bt1 - B.r01 * cp0) / B.r11 : 0.0;
-          const double cp2 = na > 2 ? (B.bt2 - B.r02 * cp0 - B.r12 * cp1) / B.r22 : 0.0;
+          const double cp0 = na > 0 ? B.bt0 * B.ir00 : 0.0;
+          const double cp1 = na > 1 ? (B.bt1 - B.r01 * cp0) * B.ir11 : 0.0;
+          const double cp2 = na > 2 ? (B.bt2 - B.r02 * cp0 - B.r12 * cp1) * B.ir22 : 0.0;
 #pragma unroll
           for (int d = 0; d < 3; ++d) u0[d] = cp0 * B.e0[d] + cp1 * B.e1[d] + cp2 * B.e2[d];
           // projector onto the free directions  M = I - sum_k e_k e_k^T, packed (xx,yy,zz,xz,yz,xy),
@@ -2100,9 +2100,9 @@ __device__ __forceinline__ void solve_env(Smem<H>& sm, const RgMpcDev* __restric
             const double g0 = -(gr[0] * B.e0[0] + gr[1] * B.e0[1] + gr[2] * B.e0[2]);
             const double g1 = -(gr[0] * B.e1[0] + gr[1] * B.e1[1] + gr[2] * B.e1[2]);
             const double g2 = -(gr[0] * B.e2[0] + gr[1] * B.e2[1] + gr[2] * B.e2[2]);
-            const double y2 = g2 / B.r22;
-            const double y1 = (g1 - B.r12 * y2) / B.r11;
-            const double y0 = (g0 - B.r01 * y1 - B.r02 * y2) / B.r00;
+            const double y2 = g2 * B.ir22;
+            const double y1 = (g1 - B.r12 * y2) * B.ir11;
+            const double y0 = (g0 - B.r01 * y1 - B.r02 * y2) * B.ir00;
             double ymin = 1e300;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
