@@ -8,6 +8,8 @@ os.environ["RG_DEBUG_TRACE"] = "2"      # start / end stamps only: the phase tim
 sys.path.insert(0, os.path.join(REPO, "robot-gym_b200")); sys.path.insert(0, REPO)
 import numpy as np, torch
 from robot_gym import cuda as rg
+from robot_gym.cuda import build as _build
+_build.build()                           # an RG_CUDA_LIB override is loaded as it is: rebuild the traced library when the sources moved
 from robot_gym.model.robots.descriptions import GHOST
 from robot_gym.util import synthetic
 
