@@ -423,7 +423,7 @@ __device__ RG_HEAVY_INLINE void cholesky_rows(SM& sm, int j_begin) {
           for (int c = 0; c <= r; ++c) if (r >= w) a[r][c] = (r == c ? 1.0 : 0.0);
       }
       // factor: l[r][c] for c < r, inverse diagonal in rd[r].  A non-positive pivot turns rd[] into NaN / inf (no clamp on
-      // the chain): one test of the product catches it, the caller gives the factorisation up (sm.flag).
+      // the chain): the test behind the panel loop catches it, the caller gives the factorisation up (sm.flag).
       double rd[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
